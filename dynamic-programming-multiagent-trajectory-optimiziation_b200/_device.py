@@ -1,0 +1,170 @@
+"""Batched device operations: thin, shape-checked wrappers over the C-ABI (include/scvx_b200.h).
+
+Inputs and outputs are torch CUDA float64 tensors in the agent-major layouts the header documents.
+torch is used for device memory and streams only; every number is produced by libscvx_b200.so.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import SolveArgs, check, load, ptr, stream_ptr
+
+F64 = torch.float64
+
+MODEL_DIMS = {_lib.MODEL_UNICYCLE: (3, 2, 2), _lib.MODEL_SINGLE_INTEGRATOR: (3, 3, 3)}
+
+
+def _dev(t):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == F64):
+        raise _lib.ScvxError("expected a float64 CUDA tensor (there is no CPU path)")
+    return t.contiguous()
+
+
+def foh(model_id, X, U, sigma, n_sub=0, out=None):
+    """FirstOrderHold.calculate_discretization for a batch (first_order_hold.py:52-87).
+
+    X (n, n_x, K), U (n, n_u, K), sigma (n,) -> A_bar (n, n_x*n_x, K-1), B_bar, C_bar (n, n_x*n_u, K-1),
+    S_bar, z_bar (n, n_x, K-1)."""
+    n_x, n_u, _ = MODEL_DIMS[model_id]
+    X, U, sigma = _dev(X), _dev(U), _dev(sigma)
+    n, _, K = X.shape
+    assert X.shape == (n, n_x, K) and U.shape == (n, n_u, K) and sigma.shape == (n,)
+    if out is None:
+        out = tuple(torch.empty((n, r, K - 1), dtype=F64, device=X.device)
+                    for r in (n_x * n_x, n_x * n_u, n_x * n_u, n_x, n_x))
+    A, B, C, S, z = out
+    check(load().scvx_foh_batched(model_id, n, K, n_sub, ptr(X), ptr(U), ptr(sigma), ptr(A), ptr(B), ptr(C),
+                                  ptr(S), ptr(z), stream_ptr()), "scvx_foh_batched")
+    return out
+
+
+def integrate_piecewise(model_id, X_lin, U, sigma, n_sub=0):
+    n_x, n_u, _ = MODEL_DIMS[model_id]
+    X_lin, U, sigma = _dev(X_lin), _dev(U), _dev(sigma)
+    n, _, K = X_lin.shape
+    out = torch.empty_like(X_lin)
+    check(load().scvx_integrate_piecewise_batched(model_id, n, K, n_sub, ptr(X_lin), ptr(U), ptr(sigma), ptr(out),
+                                                  stream_ptr()), "scvx_integrate_piecewise_batched")
+    return out
+
+
+def integrate_full(model_id, x0, U, sigma, n_sub=0):
+    n_x, n_u, _ = MODEL_DIMS[model_id]
+    x0, U, sigma = _dev(x0), _dev(U), _dev(sigma)
+    n, _, K = U.shape
+    out = torch.empty((n, n_x, K), dtype=F64, device=U.device)
+    check(load().scvx_integrate_full_batched(model_id, n, K, n_sub, ptr(x0), ptr(U), ptr(sigma), ptr(out),
+                                             stream_ptr()), "scvx_integrate_full_batched")
+    return out
+
+
+def linearize_obstacles(model_id, X_ref, obs_c, obs_clear, out=None):
+    """Obstacle half-spaces a.p + s' >= b (unicycle_model.py:103-114).
+    X_ref (n, n_x, K), obs_c (n, M, d), obs_clear (n, M) -> obs_a (n, M, d, K), obs_b (n, M, K)."""
+    _, _, d = MODEL_DIMS[model_id]
+    X_ref, obs_c, obs_clear = _dev(X_ref), _dev(obs_c), _dev(obs_clear)
+    n, _, K = X_ref.shape
+    M = obs_c.shape[1]
+    assert obs_c.shape == (n, M, d) and obs_clear.shape == (n, M)
+    if out is None:
+        out = (torch.empty((n, M, d, K), dtype=F64, device=X_ref.device),
+               torch.empty((n, M, K), dtype=F64, device=X_ref.device))
+    a, b = out
+    check(load().scvx_linearize_obstacles_batched(model_id, n, K, M, ptr(X_ref), ptr(obs_c), ptr(obs_clear), ptr(a),
+                                                  ptr(b), stream_ptr()), "scvx_linearize_obstacles_batched")
+    return out
+
+
+def linearize_collision(model_id, X_own, X_nbr, d_min, i0=0, out=None):
+    """Inter-agent half-spaces (multi_agent_model.py:61-79) between the local agents (global ids
+    i0..i0+n_local-1, references X_own) and every agent in X_nbr.
+    -> col_a (n_local, n_agents, d, K), col_b (n_local, n_agents, K); slot j == i0+i is zero."""
+    _, _, d = MODEL_DIMS[model_id]
+    X_own, X_nbr = _dev(X_own), _dev(X_nbr)
+    nl, _, K = X_own.shape
+    na = X_nbr.shape[0]
+    if out is None:
+        out = (torch.empty((nl, na, d, K), dtype=F64, device=X_own.device),
+               torch.empty((nl, na, K), dtype=F64, device=X_own.device))
+    a, b = out
+    check(load().scvx_linearize_collision_batched(model_id, nl, i0, na, K, float(d_min), ptr(X_own), ptr(X_nbr),
+                                                  ptr(a), ptr(b), stream_ptr()), "scvx_linearize_collision_batched")
+    return out
+
+
+def consensus_update(P, Y, Lam, rho):
+    """Y <- (Y+P)/2, Lam += rho (P - Y+) in place; returns per-agent (primal, dual) residual norms
+    (admm_coordinator.py:80-96, admm_utils.py:8-31).  P, Y, Lam: (n, d, K)."""
+    P, Y, Lam = _dev(P), _dev(Y), _dev(Lam)
+    n, d, K = P.shape
+    pr = torch.empty(n, dtype=F64, device=P.device)
+    du = torch.empty(n, dtype=F64, device=P.device)
+    check(load().scvx_consensus_update(n, d, K, float(rho), ptr(P), ptr(Y), ptr(Lam), ptr(pr), ptr(du), stream_ptr()),
+          "scvx_consensus_update")
+    return pr, du
+
+
+def outer_update(model_id, M, conv_tol, X_new, U_new, nu_new, sigma_new, s_prime, X, U, sigma, tr_radius, active,
+                 metrics):
+    """One on-device outer-loop bookkeeping step (scvx_solver.py:82-111, :125-133); updates X, U, sigma,
+    tr_radius, active in place and writes metrics (n, 6)."""
+    n, _, K = X.shape
+    check(load().scvx_outer_update(model_id, n, K, M, float(conv_tol), ptr(X_new), ptr(U_new), ptr(nu_new),
+                                   ptr(sigma_new), ptr(s_prime) if M > 0 else None, ptr(X), ptr(U), ptr(sigma),
+                                   ptr(tr_radius), ptr(active), ptr(metrics), stream_ptr()), "scvx_outer_update")
+
+
+class SubproblemWorkspace:
+    """Device scratch + output tensors for scvx_solve_batched, sized once for (n, K, M, n_nbr)."""
+
+    def __init__(self, model_id, n, K, M, n_nbr, device):
+        n_x, n_u, d = MODEL_DIMS[model_id]
+        self.model_id, self.n, self.K, self.M, self.n_nbr = model_id, n, K, M, n_nbr
+        nbytes = int(load().scvx_solve_workspace_bytes(model_id, n, K, M, n_nbr))
+        self.scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=device)
+        self.nbytes = nbytes
+        self.X = torch.empty((n, n_x, K), dtype=F64, device=device)
+        self.U = torch.empty((n, n_u, K), dtype=F64, device=device)
+        self.nu = torch.empty((n, n_x, K - 1), dtype=F64, device=device)
+        self.sigma = torch.empty(n, dtype=F64, device=device)
+        self.s_prime = torch.empty((n, M, K), dtype=F64, device=device)
+        self.col_slack = torch.empty((n, n_nbr, K), dtype=F64, device=device) if n_nbr else None
+        self.objective = torch.empty(n, dtype=F64, device=device)
+        self.status = torch.empty(n, dtype=torch.int32, device=device)
+        self.iters = torch.empty(n, dtype=torch.int32, device=device)
+
+
+def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_radius, x_init, x_final, pos_lo,
+                     pos_hi, v_max, w_max, obs_a, obs_b, weight_nu, weight_slack, weight_sigma,
+                     col_a=None, col_b=None, col_mask=None, quad_rho=None, lin_p=None, weight_col=1e5,
+                     max_iter=0, norm1_induced=True):
+    """SCProblem.solve / AgentSolver.solve for a batch (sc_problem.py:15-105, agent_solver.py:43-117).
+    Results land in the workspace's output tensors."""
+    a = SolveArgs()
+    a.model_id, a.n_agents, a.K, a.M, a.n_nbr = ws.model_id, ws.n, ws.K, ws.M, ws.n_nbr
+    a.max_iter, a.norm1_induced = int(max_iter), 1 if norm1_induced else 0
+    keep = []
+
+    def P(t):
+        if t is None:
+            return None
+        t = t.contiguous()
+        keep.append(t)
+        return ptr(t)
+
+    A_bar, B_bar, C_bar, S_bar, z_bar = mats
+    a.A_bar, a.B_bar, a.C_bar, a.S_bar, a.z_bar = P(A_bar), P(B_bar), P(C_bar), P(S_bar), P(z_bar)
+    a.X_ref, a.U_ref, a.sigma_ref, a.tr_radius = P(X_ref), P(U_ref), P(sigma_ref), P(tr_radius)
+    a.x_init, a.x_final, a.pos_lo, a.pos_hi, a.v_max, a.w_max = P(x_init), P(x_final), P(pos_lo), P(pos_hi), P(v_max), P(w_max)
+    a.obs_a, a.obs_b = (P(obs_a), P(obs_b)) if ws.M else (None, None)
+    a.col_a, a.col_b, a.col_mask = P(col_a), P(col_b), P(col_mask)
+    a.quad_rho, a.lin_p = P(quad_rho), P(lin_p)
+    a.weight_nu, a.weight_slack, a.weight_sigma, a.weight_col = float(weight_nu), float(weight_slack), float(weight_sigma), float(weight_col)
+    a.X, a.U, a.nu, a.sigma = ptr(ws.X), ptr(ws.U), ptr(ws.nu), ptr(ws.sigma)
+    a.s_prime = ptr(ws.s_prime) if ws.M else None
+    a.col_slack = ptr(ws.col_slack) if ws.n_nbr else None
+    a.objective, a.status, a.iters = ptr(ws.objective), ptr(ws.status), ptr(ws.iters)
+    a.workspace, a.workspace_bytes = ptr(ws.scratch), ws.nbytes
+    check(load().scvx_solve_batched(ctypes.byref(a), stream_ptr()), "scvx_solve_batched")
+    return ws

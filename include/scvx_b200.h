@@ -1,0 +1,178 @@
+/*
+ * scvx_b200.h -- C-ABI of the B200-native SCvx inner loop (libscvx_b200.so).
+ *
+ * Drop-in boundary for the hot path of
+ *   shiivashaakeri/Dynamic-Programming-MultiAgent-Trajectory-Optimiziation
+ * (paths below are relative to that repository).  The reference has no FFI of its own -- its
+ * "operator API" is a set of Python classes -- so each entry point names the Python method whose
+ * arithmetic it replaces; the Python mirror in scvx_b200/ binds these with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C types only; every array pointer is a DEVICE pointer (cudaMalloc / torch CUDA tensor)
+ *     unless the parameter name ends in _h (host).  `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream).  Nothing here allocates device memory except the explicit
+ *     workspace-size query + caller-provided workspace, and the *_host convenience calls.
+ *   - all arithmetic is IEEE fp64.
+ *   - batched layout is agent-major, then the reference's own per-agent numpy layout, C-order:
+ *       X      [n_agents][n_x][K]          (numpy (n_x, K) per agent)
+ *       U      [n_agents][n_u][K]
+ *       A_bar  [n_agents][n_x*n_x][K-1]    column k = Phi_k flattened order='F'
+ *       B_bar  [n_agents][n_x*n_u][K-1]    C_bar likewise;  S_bar, z_bar [n_agents][n_x][K-1]
+ *     so a batch-of-1 slice is bit-compatible with the arrays the reference produces.
+ *   - return value: 0 on success, negative SCVX_E_* on error (nothing is written on argument errors).
+ *     Per-agent solver outcomes are written to `status` arrays (SCVX_ST_*).
+ *   - thread-safety: calls are re-entrant; concurrent calls must use distinct streams/workspaces.
+ */
+#ifndef SCVX_B200_H
+#define SCVX_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCVX_ABI_VERSION 1
+
+/* model ids (SCvx/models/unicycle_model.py, SCvx/models/single_integrator_model.py) */
+#define SCVX_MODEL_UNICYCLE 0           /* n_x=3 n_u=2 d=2 */
+#define SCVX_MODEL_SINGLE_INTEGRATOR 1  /* n_x=3 n_u=3 d=3 */
+
+/* error codes */
+#define SCVX_OK 0
+#define SCVX_E_BADARG (-1)
+#define SCVX_E_CUDA (-2)
+#define SCVX_E_WORKSPACE (-3)
+#define SCVX_E_UNSUPPORTED (-4)
+
+/* per-agent solver status words */
+#define SCVX_ST_OPTIMAL 0
+#define SCVX_ST_MAXITER 1
+#define SCVX_ST_NUMERICAL 2   /* NaN / non-positive pivot that regularisation could not repair */
+
+int scvx_abi_version(void);
+/* last CUDA error string seen by this library on the calling thread (never NULL) */
+const char* scvx_last_error(void);
+/* n_x, n_u, position dimension d of a model id; returns SCVX_E_BADARG for unknown ids */
+int scvx_model_dims(int model_id, int* n_x, int* n_u, int* d);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 1 -- first-order-hold discretisation.
+ * Replaces FirstOrderHold.calculate_discretization (SCvx/discretization/first_order_hold.py:52-87)
+ * and its right-hand side _ode_dVdt (:89-125), for a whole batch of agents at once.
+ * One thread integrates one (agent, interval) with classical RK4, n_sub sub-steps over [0, dt],
+ * dt = 1/(K-1).  n_sub = 0 selects the sub-step count per interval on the device from
+ * sigma*dt*max(1,|u|) so that the result is within ~1e-10 relative of the exact ODE solution.
+ * sigma: [n_agents].
+ */
+int scvx_foh_batched(int model_id, int n_agents, int K, int n_sub,
+                     const double* X, const double* U, const double* sigma,
+                     double* A_bar, double* B_bar, double* C_bar, double* S_bar, double* z_bar,
+                     void* stream);
+
+/* FirstOrderHold.integrate_nonlinear_piecewise (first_order_hold.py:127-140): X_nl[:,0]=X_lin[:,0],
+ * X_nl[:,k+1] = flow of xdot=f(x,u(t)) over [0, dt*sigma] from X_lin[:,k].  X_nl: [n_agents][n_x][K]. */
+int scvx_integrate_piecewise_batched(int model_id, int n_agents, int K, int n_sub,
+                                     const double* X_lin, const double* U, const double* sigma,
+                                     double* X_nl, void* stream);
+/* FirstOrderHold.integrate_nonlinear_full (first_order_hold.py:142-155): x0 [n_agents][n_x]. */
+int scvx_integrate_full_batched(int model_id, int n_agents, int K, int n_sub,
+                                const double* x0, const double* U, const double* sigma,
+                                double* X_nl, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 2 -- constraint linearisation.
+ *
+ * Obstacle half-spaces (UnicycleModel.get_constraints, SCvx/models/unicycle_model.py:103-114;
+ * SingleIntegratorModel twin, single_integrator_model.py:113-126):
+ *   a_jk = (p_ref_k - c_j) / (||p_ref_k - c_j||_2 + 1e-6),   b_jk = clearance_j + a_jk . c_j
+ *   so that the constraint reads  a_jk . p_k + s'_jk >= b_jk.
+ * obs_c [n_agents][M][d], obs_clear [n_agents][M] (= r_j + r_rob (+margin));
+ * out: obs_a [n_agents][M][d][K], obs_b [n_agents][M][K].
+ */
+int scvx_linearize_obstacles_batched(int model_id, int n_agents, int K, int M,
+                                     const double* X_ref, const double* obs_c, const double* obs_clear,
+                                     double* obs_a, double* obs_b, void* stream);
+
+/* Inter-agent half-spaces (MultiAgentModel.linearize_collision, SCvx/models/multi_agent_model.py:61-79;
+ * SI_MultiAgentModel.linearize_inter_agent_collision, SI_multi_agent_model.py:49-74), all ordered pairs
+ * between `n_local` agents (global ids i0..i0+n_local-1) and all n_agents neighbours:
+ *   a_ijk = (p_i,k - q_j,k)/(||.||_2 + 1e-6),   b_ijk = d_min + a_ijk . q_j,k
+ * X_own [n_local][n_x][K] are the linearisation references of the local agents; X_nbr
+ * [n_agents][n_x][K] the neighbours' current trajectories.  Slot j==i0+i is written as zeros.
+ * out: col_a [n_local][n_agents][d][K], col_b [n_local][n_agents][K].
+ */
+int scvx_linearize_collision_batched(int model_id, int n_local, int i0, int n_agents, int K, double d_min,
+                                     const double* X_own, const double* X_nbr,
+                                     double* col_a, double* col_b, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage 3 -- convex sub-problem, batched.
+ * Replaces SCProblem.solve (SCvx/optimization/sc_problem.py:15-105, problem statement :21-83 with the
+ * model rows of unicycle_model.py:85-115 / single_integrator_model.py:79-128) and, when n_nbr > 0,
+ * AgentSolver.setup+solve (SCvx/optimization/agent_solver.py:43-117).  cvxpy+ECOS is replaced by a
+ * structure-exploiting primal-dual interior-point method, one thread block per agent, block-tridiagonal
+ * KKT factor resident in shared memory.  See DESIGN.md for the formulation.
+ *
+ * All per-agent inputs are arrays over agents.  Scalars that the reference keeps global
+ * (weights) are passed per call.
+ */
+typedef struct scvx_solve_args {
+  int model_id, n_agents, K;
+  int M;             /* obstacles per agent (half-space tables below) */
+  int n_nbr;         /* inter-agent half-space slots per agent (0 = plain SCProblem) */
+  int max_iter;      /* IPM iteration cap (<=0: default 60) */
+  int norm1_induced; /* 1: cvxpy matrix 1-norm (max column abs-sum) -- the reference's semantics */
+  /* FOH matrices (stage 1 output layout) */
+  const double *A_bar, *B_bar, *C_bar, *S_bar, *z_bar;
+  /* trust-region centre */
+  const double *X_ref, *U_ref, *sigma_ref;        /* [n][n_x][K], [n][n_u][K], [n] */
+  const double *tr_radius;                        /* [n] */
+  /* boundary conditions and bounds */
+  const double *x_init, *x_final;                 /* [n][n_x] */
+  const double *pos_lo, *pos_hi;                  /* [n]  (lower_bound + r_rob, upper_bound - r_rob) */
+  const double *v_max, *w_max;                    /* [n]  (w_max ignored for the single integrator) */
+  /* obstacle half-spaces  a.p + s' >= b  (stage 2 layout) */
+  const double *obs_a, *obs_b;                    /* [n][M][d][K], [n][M][K] */
+  /* inter-agent half-spaces a.(p - Y) + S >= d_min  <=>  a.p + S >= b  with b = d_min + a.Y */
+  const double *col_a, *col_b;                    /* [n][n_nbr][d][K], [n][n_nbr][K] */
+  const unsigned char *col_mask;                  /* [n][n_nbr] 1 = slot active (NULL: all active) */
+  /* augmented-Lagrangian terms on positions: quad_rho/2 * ||P||^2 + <lin_p, P>  */
+  const double *quad_rho;                         /* [n] or NULL */
+  const double *lin_p;                            /* [n][d][K] or NULL */
+  double weight_nu, weight_slack, weight_sigma, weight_col;
+  /* outputs */
+  double *X, *U, *nu, *sigma;                     /* [n][n_x][K], [n][n_u][K], [n][n_x][K-1], [n] */
+  double *s_prime;                                /* [n][M][K]  obstacle slacks (hinge values) */
+  double *col_slack;                              /* [n][n_nbr][K] or NULL */
+  double *objective;                              /* [n] objective value incl. slack terms */
+  int *status, *iters;                            /* [n] */
+  /* scratch */
+  void* workspace; unsigned long long workspace_bytes;
+} scvx_solve_args;
+
+/* bytes of device workspace scvx_solve_batched needs for these sizes */
+unsigned long long scvx_solve_workspace_bytes(int model_id, int n_agents, int K, int M, int n_nbr);
+int scvx_solve_batched(const scvx_solve_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Consensus round (ADMMCoordinator.solve, SCvx/optimization/admm_coordinator.py:80-96 and
+ * admm_utils.py:8-31):  Y+ = (Y + P)/2;  Lambda += rho (P - Y+);
+ * pr[j] = ||P_j - Y+_j||_F, du[j] = ||Y+_j - Y_j||_F.   P, Y, Lambda: [n_agents][d][K] (in place).
+ */
+int scvx_consensus_update(int n_agents, int d, int K, double rho, const double* P,
+                          double* Y, double* Lambda, double* pr, double* du, void* stream);
+
+/* On-device SCvx bookkeeping for one outer iteration of a batch (SCVXSolver.solve,
+ * SCvx/optimization/scvx_solver.py:82-111, :125-133): metrics, convergence flag, trust-region update and
+ * iterate acceptance, without a host round trip.  metrics: [n_agents][6] = nu_norm, slack_norm, dx, du, ds, sigma_new.
+ * `active` [n_agents] (1 = still iterating) is updated in place; converged agents keep their OLD iterate.
+ */
+int scvx_outer_update(int model_id, int n_agents, int K, int M, double conv_tol,
+                      const double* X_new, const double* U_new, const double* nu_new, const double* sigma_new,
+                      const double* s_prime, double* X, double* U, double* sigma, double* tr_radius,
+                      int* active, double* metrics, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCVX_B200_H */

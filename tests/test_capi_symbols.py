@@ -1,0 +1,56 @@
+"""The C-ABI library loads and exports every symbol include/scvx_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "scvx_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(scvx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_entry_points():
+    names = _declared()
+    for must in ("scvx_foh_batched", "scvx_linearize_obstacles_batched", "scvx_linearize_collision_batched",
+                 "scvx_solve_batched", "scvx_consensus_update", "scvx_outer_update"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+    __graft_entry__.build()
+    from scvx_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH)
+    try:
+        lib = ctypes.CDLL(_lib.LIB_PATH)
+    except OSError as e:   # e.g. libcudart not resolvable on a CPU-only box
+        pytest.skip(f"cannot dlopen without CUDA runtime: {e}")
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(_lib.SIGNATURES) == set(_declared())
+    assert lib.scvx_abi_version() == 1
+    nx, nu, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.scvx_model_dims(0, ctypes.byref(nx), ctypes.byref(nu), ctypes.byref(d)) == 0
+    assert (nx.value, nu.value, d.value) == (3, 2, 2)
+    assert lib.scvx_model_dims(99, None, None, None) == -1
+
+
+def test_solve_args_struct_matches_header():
+    """Field order of the ctypes mirror == field order of `scvx_solve_args` in the header."""
+    from scvx_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "scvx_b200.h")).read()
+    body = re.search(r"typedef struct scvx_solve_args \{(.*?)\} scvx_solve_args;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for stmt in body.split(";"):
+        stmt = stmt.strip()
+        if not stmt:
+            continue
+        stmt = re.sub(r"^(const\s+)?(unsigned\s+long\s+long|unsigned\s+char|double|int|void)\s*", "", stmt)
+        fields += [f.strip().lstrip("*").strip() for f in stmt.split(",")]
+    assert fields == [f[0] for f in _lib.SolveArgs._fields_]

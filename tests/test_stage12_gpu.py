@@ -1,0 +1,271 @@
+"""GPU parity: stage 1 (FOH RK4 kernel), stage 2 (linearisation kernels), consensus and outer-loop
+bookkeeping kernels, all through the C-ABI, against the CPU oracle and the committed golden vectors.
+
+Tolerances (north_star): discretisation matrices within 1e-9 RELATIVE (to the max-norm of each array)
+of the reference's ODE right-hand side integrated tightly (rtol=1e-13); agreement with the reference's
+own default-tolerance odeint output is reported at its intrinsic ~1e-7 level.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import foh as ofoh, models as omodels, scvx as oscvx
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9
+
+
+def rel_err(got, want):
+    return float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-300))
+
+
+def _t(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+# ---- stage 1 -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["s1", "s24"])
+def test_foh_golden_unicycle(cuda, golden, tag):
+    from scvx_b200.discretization.first_order_hold import FirstOrderHold
+    from scvx_b200.models.unicycle_model import UnicycleModel
+    X, U, s = golden[f"uni_{tag}_X"], golden[f"uni_{tag}_U"], float(golden[f"uni_{tag}_sigma"])
+    foh = FirstOrderHold(UnicycleModel(), 50)
+    out = foh.calculate_discretization(X, U, s)
+    for nm, arr in zip("ABCSz", out):
+        assert rel_err(arr, golden[f"uni_{tag}_tight_{nm}"]) < REL_TOL, nm
+        # vs the reference's default-tolerance odeint output: its own error level
+        assert rel_err(arr, golden[f"uni_{tag}_ref_{nm}"]) < 5e-7, nm
+    # shapes as asserted by SCvx/tests/test_disc.py:9-27
+    assert out[0].shape == (9, 49) and out[1].shape == (6, 49) and out[2].shape == (6, 49)
+    assert out[3].shape == (3, 49) and out[4].shape == (3, 49)
+    # aliasing behaviour of the reference (first_order_hold.py:20-24,87)
+    out2 = foh.calculate_discretization(X, U, s)
+    assert out2[0] is out[0]
+
+
+def test_foh_golden_single_integrator(cuda, golden):
+    from scvx_b200.discretization.first_order_hold import FirstOrderHold
+    from scvx_b200.models.single_integrator_model import SingleIntegratorModel
+    X, U, s = golden["si_X"], golden["si_U"], float(golden["si_sigma"])
+    foh = FirstOrderHold(SingleIntegratorModel(), 20)
+    out = foh.calculate_discretization(X, U, s)
+    for nm, arr in zip("ABCSz", out):
+        assert rel_err(arr, golden[f"si_tight_{nm}"]) < REL_TOL, nm
+    dt = 1.0 / 19
+    np.testing.assert_allclose(out[1][:, 0], (s * dt / 2 * np.eye(3)).reshape(-1), atol=1e-12)
+    nl = foh.integrate_nonlinear_piecewise(X, U, s)
+    assert rel_err(nl, golden["si_nl_piecewise"]) < 1e-7
+
+
+def test_foh_warm_start_iteration0(cuda, golden):
+    from scvx_b200.discretization.first_order_hold import FirstOrderHold
+    from scvx_b200.models.unicycle_model import UnicycleModel
+    m = UnicycleModel()
+    X, U = m.initialize_trajectory(np.zeros((3, 50)), np.zeros((2, 50)))
+    np.testing.assert_array_equal(X, golden["uni_init_X"])
+    out = FirstOrderHold(m, 50).calculate_discretization(X, U, 1.0)
+    for nm, arr in zip("ABCSz", out):
+        assert rel_err(arr, golden[f"uni_init_ref_{nm}"]) < 1e-8, nm
+
+
+def test_nonlinear_integrators(cuda, golden):
+    from scvx_b200.discretization.first_order_hold import FirstOrderHold
+    from scvx_b200.models.unicycle_model import UnicycleModel
+    X, U, s = golden["uni_s24_X"], golden["uni_s24_U"], float(golden["uni_s24_sigma"])
+    foh = FirstOrderHold(UnicycleModel(), 50)
+    F = ofoh.OracleFOH(omodels.unicycle(), 50)
+    assert rel_err(foh.integrate_nonlinear_piecewise(X, U, s), F.integrate_nonlinear_piecewise(X, U, s, tol="tight")) < REL_TOL
+    assert rel_err(foh.integrate_nonlinear_full(X[:, 0], U, s), F.integrate_nonlinear_full(X[:, 0], U, s, tol="tight")) < REL_TOL
+    assert foh.integrate_nonlinear_piecewise(X, U, s).shape == (3, 50)
+
+
+@pytest.mark.parametrize("kind,K,n", [("unicycle", 100, 7), ("single_integrator", 33, 5), ("unicycle", 2, 3)])
+def test_foh_batched_random_vs_oracle(cuda, kind, K, n):
+    """Batched entry point on seeded random inputs, ragged sizes (n not a multiple of anything, K=2 edge)."""
+    from scvx_b200 import _device, _lib
+    rng = np.random.default_rng(K * 1000 + n)
+    if kind == "unicycle":
+        om, mid, n_u = omodels.unicycle(), _lib.MODEL_UNICYCLE, 2
+    else:
+        om, mid, n_u = omodels.single_integrator(), _lib.MODEL_SINGLE_INTEGRATOR, 3
+    X = rng.uniform(-8, 8, (n, 3, K)); X[:, 2] = rng.uniform(-3, 3, (n, K))
+    U = rng.uniform(-1, 1, (n, n_u, K))
+    sig = rng.uniform(0.5, 30.0, n)
+    out = _device.foh(mid, _t(X, cuda), _t(U, cuda), _t(sig, cuda))
+    F = ofoh.OracleFOH(om, K)
+    for a in range(n):
+        want = F.calculate_discretization(X[a], U[a], sig[a], tol="tight")
+        for nm, g, w in zip("ABCSz", out, want):
+            assert rel_err(g[a].cpu().numpy(), w) < REL_TOL, (a, nm)
+
+
+def test_foh_fixed_substeps_converge_4th_order(cuda, golden):
+    """RK4: halving h must cut the error ~16x (size-independent property of the integrator)."""
+    from scvx_b200 import _device, _lib
+    X, U, s = golden["uni_s24_X"], golden["uni_s24_U"], float(golden["uni_s24_sigma"])
+    Xd, Ud, sd = _t(X[None], cuda), _t(U[None], cuda), _t(np.array([s]), cuda)
+    errs = []
+    for ns in (4, 8, 16):
+        out = _device.foh(_lib.MODEL_UNICYCLE, Xd, Ud, sd, n_sub=ns)
+        errs.append(max(rel_err(g[0].cpu().numpy(), golden[f"uni_s24_tight_{nm}"]) for nm, g in zip("ABCSz", out)))
+    assert 10 < errs[0] / errs[1] < 24 and 10 < errs[1] / errs[2] < 24, errs
+
+
+def test_foh_empty_batch_and_bad_args(cuda):
+    from scvx_b200 import _device, _lib
+    out = _device.foh(_lib.MODEL_UNICYCLE, torch.empty((0, 3, 10), dtype=torch.float64, device=cuda),
+                      torch.empty((0, 2, 10), dtype=torch.float64, device=cuda),
+                      torch.empty((0,), dtype=torch.float64, device=cuda))
+    assert out[0].shape == (0, 9, 9)
+    lib = _lib.load()
+    assert lib.scvx_foh_batched(7, 1, 10, 0, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.scvx_foh_batched(0, 1, 1, 0, None, None, None, None, None, None, None, None, None) == -1
+    assert b"bad argument" in lib.scvx_last_error()
+    with pytest.raises(_lib.ScvxError):
+        _device.foh(_lib.MODEL_UNICYCLE, torch.zeros((1, 3, 10), dtype=torch.float64), torch.zeros((1, 2, 10), dtype=torch.float64),
+                    torch.zeros(1, dtype=torch.float64))     # CPU tensors: no CPU path
+
+
+def test_foh_full_size_properties(cuda):
+    """BASELINE config 2 size (1024 agents x K=100): size-independent properties.
+    (i) zero control => f=0, A=0: Phi = I, S_bar = z_bar = 0, B_bar + C_bar = sigma*dt*B(theta);
+    (ii) agent-permutation equivariance; (iii) single integrator closed form."""
+    from scvx_b200 import _device, _lib
+    n, K = 1024, 100
+    rng = np.random.default_rng(2)
+    X = rng.uniform(-8, 8, (n, 3, K)); U0 = np.zeros((n, 2, K)); sig = rng.uniform(1, 30, n)
+    A, B, C, S, z = [o.cpu().numpy() for o in _device.foh(_lib.MODEL_UNICYCLE, _t(X, cuda), _t(U0, cuda), _t(sig, cuda))]
+    np.testing.assert_allclose(A, np.broadcast_to(np.eye(3).reshape(-1, order="F")[None, :, None], A.shape), atol=1e-14)
+    assert np.abs(S).max() < 1e-14 and np.abs(z).max() < 1e-14
+    dt = 1.0 / (K - 1)
+    th = X[:, 2, :-1]
+    BC = B + C
+    np.testing.assert_allclose(BC[:, 0], sig[:, None] * dt * np.cos(th), atol=1e-12)
+    np.testing.assert_allclose(BC[:, 1], sig[:, None] * dt * np.sin(th), atol=1e-12)
+    np.testing.assert_allclose(BC[:, 5], np.broadcast_to(sig[:, None] * dt, th.shape), atol=1e-12)
+    U = rng.uniform(-1, 1, (n, 2, K))
+    perm = rng.permutation(n)
+    o1 = _device.foh(_lib.MODEL_UNICYCLE, _t(X, cuda), _t(U, cuda), _t(sig, cuda))
+    o2 = _device.foh(_lib.MODEL_UNICYCLE, _t(X[perm], cuda), _t(U[perm], cuda), _t(sig[perm], cuda))
+    for a, b in zip(o1, o2):
+        assert torch.equal(a[torch.as_tensor(perm, device=cuda)], b)
+    U3 = rng.uniform(-1, 1, (n, 3, K))
+    A, B, C, S, z = [o.cpu().numpy() for o in _device.foh(_lib.MODEL_SINGLE_INTEGRATOR, _t(X, cuda), _t(U3, cuda), _t(sig, cuda))]
+    np.testing.assert_allclose(B[:, 0], np.broadcast_to(sig[:, None] * dt / 2, B[:, 0].shape), rtol=1e-12)
+    np.testing.assert_allclose(S, dt * (U3[:, :, :-1] + U3[:, :, 1:]) / 2, atol=1e-13)
+    np.testing.assert_allclose(z, -sig[:, None, None] * S, atol=1e-12)
+
+
+# ---- stage 2 -------------------------------------------------------------------------------------
+def test_collision_golden_and_known_answer(cuda, golden):
+    from scvx_b200.global_parameters import K
+    from scvx_b200.models.multi_agent_model import MultiAgentModel
+    from scvx_b200.models.SI_multi_agent_model import SI_MultiAgentModel
+    mam = MultiAgentModel([{"r_init": np.zeros(3), "r_final": np.ones(3)}] * 2, d_min=float(golden["col2_dmin"]))
+    A, b = mam.linearize_collision(0, 1, golden["col2_Xi"], golden["col2_Xj"])
+    np.testing.assert_allclose(A, golden["col2_A"], rtol=0, atol=1e-15)   # incl. the coincident column (diff = 0)
+    np.testing.assert_allclose(b, golden["col2_b"], rtol=0, atol=1e-14)
+    smam = SI_MultiAgentModel([{"r_init": np.zeros(3), "r_final": np.ones(3)}] * 2, d_min=float(golden["col3_dmin"]))
+    A, b = smam.linearize_inter_agent_collision(0, 1, golden["col3_Xi"], golden["col3_Xj"])
+    np.testing.assert_allclose(A, golden["col3_A"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(b, golden["col3_b"], rtol=0, atol=1e-14)
+    # the reference's own known-answer test (SCvx/multi_agent_tests/test_multi_agent_model.py:42-59)
+    d_min = 2.0
+    mam = MultiAgentModel([{"r_init": np.array([0, d_min, 0]), "r_final": np.array([0, d_min, 0])},
+                           {"r_init": np.zeros(3), "r_final": np.zeros(3)}], d_min=d_min)
+    assert mam.N == 2 and mam.d_min == d_min
+    Xi = np.tile(np.array([[0.0], [d_min], [0.0]]), (1, K)); Xj = np.zeros((3, K))
+    A_ij, b_ij = mam.linearize_collision(0, 1, Xi, Xj)
+    for k in range(K):
+        assert np.allclose(A_ij[:, k], [0.0, 1.0], atol=1e-6)
+        assert b_ij[k] == pytest.approx(d_min, rel=1e-6)
+
+
+@pytest.mark.parametrize("kind,d", [("unicycle", 2), ("single_integrator", 3)])
+def test_collision_all_pairs_batched(cuda, kind, d):
+    from scvx_b200 import _device, _lib
+    mid = _lib.MODEL_UNICYCLE if d == 2 else _lib.MODEL_SINGLE_INTEGRATOR
+    N, K, i0, nl = 19, 37, 5, 6
+    rng = np.random.default_rng(3)
+    Xall = rng.uniform(-5, 5, (N, 3, K))
+    Xown = rng.uniform(-5, 5, (nl, 3, K))
+    a, b = _device.linearize_collision(mid, _t(Xown, cuda), _t(Xall, cuda), 0.5, i0=i0)
+    a, b = a.cpu().numpy(), b.cpu().numpy()
+    for i in range(nl):
+        for j in range(N):
+            if j == i0 + i:
+                assert not a[i, j].any() and not b[i, j].any()
+                continue
+            A_ij, b_ij = omodels.linearize_collision(d, 0.5, Xown[i], Xall[j])
+            np.testing.assert_allclose(a[i, j], A_ij, rtol=0, atol=1e-15)
+            np.testing.assert_allclose(b[i, j], b_ij, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("kind", ["unicycle", "single_integrator"])
+def test_obstacle_linearisation(cuda, kind):
+    from scvx_b200 import _device, _lib
+    om = omodels.unicycle() if kind == "unicycle" else omodels.single_integrator()
+    mid = _lib.MODEL_UNICYCLE if kind == "unicycle" else _lib.MODEL_SINGLE_INTEGRATOR
+    n, K, M, d = 3, 41, len(om.obstacles), om.d
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-8, 8, (n, 3, K))
+    X[0, 0:d, 3] = om.obstacles[0][0]         # reference point exactly at a centre: a = 0/(0+1e-6) = 0
+    ctr = np.tile(np.array([c for c, _ in om.obstacles])[None], (n, 1, 1))
+    clr = np.tile(np.array([om.obstacle_clearance(j) for j in range(M)])[None], (n, 1))
+    a, b = _device.linearize_obstacles(mid, _t(X, cuda), _t(ctr, cuda), _t(clr, cuda))
+    for i in range(n):
+        wa, wrhs, wc = omodels.linearize_obstacles(om, X[i])
+        np.testing.assert_allclose(a[i].cpu().numpy(), wa, rtol=0, atol=1e-15)
+        wb = wrhs[:, None] + np.einsum("mdk,md->mk", wa, wc)
+        np.testing.assert_allclose(b[i].cpu().numpy(), wb, rtol=0, atol=1e-13)
+
+
+# ---- consensus + outer bookkeeping ---------------------------------------------------------------------
+def test_consensus_update(cuda):
+    from scvx_b200 import _device
+    n, d, K, rho = 11, 3, 100, 1.7
+    rng = np.random.default_rng(9)
+    P, Y, L = rng.normal(size=(n, d, K)), rng.normal(size=(n, d, K)), rng.normal(size=(n, d, K))
+    Yd, Ld = _t(Y, cuda), _t(L, cuda)
+    pr, du = _device.consensus_update(_t(P, cuda), Yd, Ld, rho)
+    Yn = 0.5 * (Y + P)
+    np.testing.assert_allclose(Yd.cpu().numpy(), Yn, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(Ld.cpu().numpy(), L + rho * (P - Yn), rtol=0, atol=1e-14)
+    for j in range(n):
+        assert pr[j].item() == pytest.approx(oscvx.primal_residual(P[j], Yn[j]), rel=1e-13)
+        assert du[j].item() == pytest.approx(oscvx.dual_residual(Yn[j], Y[j]), rel=1e-13)
+
+
+def test_outer_update(cuda):
+    """scvx_solver.py:82-111,125-133: metrics, converged agents keep the OLD iterate, grow-only trust region."""
+    from scvx_b200 import _device, _lib
+    n, K, M = 4, 30, 2
+    rng = np.random.default_rng(11)
+    X, U, sig = rng.normal(size=(n, 3, K)), rng.normal(size=(n, 2, K)), np.array([3.0, 4.0, 5.0, 6.0])
+    Xn, Un, sn = X + rng.normal(size=X.shape), U + rng.normal(size=U.shape), sig + 1.0
+    nu = rng.normal(size=(n, 3, K - 1)); sp = np.abs(rng.normal(size=(n, M, K)))
+    # agent 1: converged (tiny change, no defect, no slack); agent 2: low defect/slack but moved; agent 3: inactive
+    Xn[1], Un[1], sn[1], nu[1], sp[1] = X[1] + 1e-6, U[1], sig[1] + 1e-5, 1e-6, 0.0
+    nu[2], sp[2] = 1e-4, 1e-5
+    tr = np.array([100.0, 10.0, 40.0, 7.0]); active = np.array([1, 1, 1, 0], dtype=np.int32)
+    Xd, Ud, sd, trd = _t(X, cuda), _t(U, cuda), _t(sig, cuda), _t(tr, cuda)
+    act = torch.as_tensor(active).to(cuda); met = torch.zeros((n, 6), dtype=torch.float64, device=cuda)
+    _device.outer_update(_lib.MODEL_UNICYCLE, M, 1e-3, _t(Xn, cuda), _t(Un, cuda), _t(nu, cuda), _t(sn, cuda), _t(sp, cuda),
+                         Xd, Ud, sd, trd, act, met)
+    met = met.cpu().numpy()
+    for a in range(3):
+        assert met[a, 0] == pytest.approx(np.linalg.norm(nu[a], 1), rel=1e-13)
+        assert met[a, 1] == pytest.approx(sp[a].sum(), rel=1e-13, abs=1e-300)
+        assert met[a, 2] == pytest.approx(np.linalg.norm(Xn[a] - X[a]), rel=1e-12)
+        assert met[a, 3] == pytest.approx(np.linalg.norm(Un[a] - U[a]), rel=1e-12, abs=1e-300)
+        assert met[a, 4] == pytest.approx(abs(sn[a] - sig[a]), rel=1e-12)
+        assert met[a, 5] == sn[a]
+    assert act.cpu().tolist() == [1, 0, 1, 0]
+    np.testing.assert_array_equal(Xd[0].cpu().numpy(), Xn[0])
+    np.testing.assert_array_equal(Xd[1].cpu().numpy(), X[1])       # converged: previous iterate kept
+    np.testing.assert_array_equal(Xd[3].cpu().numpy(), X[3])       # inactive: untouched
+    assert sd.cpu().tolist() == [sn[0], sig[1], sn[2], sig[3]]
+    assert trd.cpu().tolist() == [oscvx.update_trust_region(100.0, met[0, 0], met[0, 1]), 10.0,
+                                  oscvx.update_trust_region(40.0, met[2, 0], met[2, 1]), 7.0]
+    assert trd[0].item() == 50.0 and trd[2].item() == 50.0
