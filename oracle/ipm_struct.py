@@ -1,0 +1,345 @@
+"""CPU twin of the GPU sub-problem solver's ALGORITHM (csrc/solver.cu) -- TEST INFRASTRUCTURE ONLY.
+
+This is not a restatement of reference code: the reference hands the sub-problem to cvxpy+ECOS
+(scvx_solver.py:71).  It restates, in numpy, the structure-exploiting primal-dual interior-point
+method that the CUDA kernel implements (same formulation, same block-tridiagonal + border
+elimination, same Mehrotra predictor-corrector), so that (i) the algorithm could be validated against
+the exact HiGHS oracle (oracle/subproblem.py) before any CUDA was written and (ii) kernel bugs can be
+bisected iterate by iterate.  The problem statement it solves is SURVEY Appendix A.1/A.3
+(sc_problem.py:21-83, unicycle_model.py:85-115, single_integrator_model.py:79-128,
+agent_solver.py:79-102).
+
+Formulation (per agent), z = (w_0..w_{K-1}, sigma, t_nu, t_x, t_u), w_k = (x_k, u_k):
+  min  c_s [ w_nu t_nu + w_sig sigma + sum_hinge w_h max(0, b - a.p_k) + rho/2 |P|^2 + <lin, P> ]
+  s.t. e.nu_k(z) - t_nu <= 0          for all sign patterns e in {+-1}^{n_x}, k = 0..K-2   (|nu_k|_1 <= t_nu)
+       e.(x_k - xref_k) - t_x <= 0    for all e, k                                          (|dx_k|_1 <= t_x)
+       e.(u_k - uref_k) - t_u <= 0    for all e, k
+       t_x + t_u +- (sigma - sigma_ref) <= r ;  -sigma <= 0
+       pos_lo <= p_k <= pos_hi ;  unicycle: 0 <= v_k <= v_max, |w_k| <= w_max ;  SI: 1/2(|u_k|^2 - v_max^2) <= 0
+       w_0, w_{K-1} fixed (boundary conditions).
+  Hinge terms are handled with a private slack xi per row that is eliminated analytically from the
+  Newton system (2 inequality rows per hinge: -a.p - xi <= -b, -xi <= 0).
+"""
+from __future__ import annotations
+
+import itertools
+
+import numpy as np
+
+from . import subproblem as spb
+
+
+def _signs(n):
+    return np.array(list(itertools.product([1.0, -1.0], repeat=n)))[:, ::-1].copy()   # bit i of e -> sign of comp i
+
+
+class StructIPM:
+    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False):
+        self.p, self.verbose = p, verbose
+        self.mu0, self.max_iter, self.eps_gap, self.eps_feas = mu0, max_iter, eps_gap, eps_feas
+        m, K = p.model, p.K
+        self.K, self.nx, self.nu, self.d = K, m.n_x, m.n_u, m.d
+        self.ns = self.nx + self.nu
+        self.ball = (m.kind != "unicycle")
+        nx, nu = self.nx, self.nu
+        # interval Jacobians: nu_k = Jn_k w_{k+1} + Jp_k w_k + Js_k sigma - zbar_k
+        self.Jp = np.zeros((K - 1, nx, self.ns)); self.Jn = np.zeros((K - 1, nx, self.ns)); self.Js = np.zeros((K - 1, nx))
+        for k in range(K - 1):
+            A = p.A_bar[:, k].reshape((nx, nx), order="F"); B = p.B_bar[:, k].reshape((nx, nu), order="F")
+            C = p.C_bar[:, k].reshape((nx, nu), order="F")
+            self.Jp[k, :, :nx] = -A; self.Jp[k, :, nx:] = -B
+            self.Jn[k, :, :nx] = np.eye(nx); self.Jn[k, :, nx:] = -C
+            self.Js[k] = -p.S_bar[:, k]
+        self.Ex, self.Eu = _signs(nx), _signs(nu)
+        # cost scaling
+        self.cs = 1.0 / max(p.weight_nu, p.weight_sigma, 1e-300)
+        # hinge tables: a (nh, d, K), b (nh, K), w (nh,)
+        a_list, b_list, w_list = [], [], []
+        for j in range(len(m.obstacles)):
+            a_list.append(p.obs_a[j]); b_list.append(p.obs_rhs[j] + np.einsum("dk,d->k", p.obs_a[j], p.obs_c[j]))
+            w_list.append(p.weight_slack)
+        for nb in p.neighbors:
+            a_list.append(nb["a"]); b_list.append(p.d_min + np.einsum("dk,dk->k", nb["a"], nb["Y"])); w_list.append(p.weight_col)
+        self.nh = len(a_list)
+        self.ha = np.array(a_list).reshape(self.nh, self.d, K)
+        self.hb = np.array(b_list).reshape(self.nh, K)
+        self.hw = np.array(w_list).reshape(self.nh) * self.cs
+        # quadratic / linear position terms (ADMM variant)
+        self.qrho = 0.0; self.qlin = np.zeros((self.d, K))
+        for nb in p.neighbors:
+            self.qrho += p.rho
+            self.qlin += nb["Lam"] - p.rho * nb["Y"]
+        self.qrho *= self.cs; self.qlin *= self.cs
+        self.c_sig = p.weight_sigma * self.cs; self.c_tnu = p.weight_nu * self.cs
+        lo_p, hi_p = m.lower_bound + m.robot_radius, m.upper_bound - m.robot_radius
+        self.lo_p, self.hi_p = lo_p, hi_p
+
+    # ------------------------------------------------------------------------------------------
+    def _nu(self, W, sig):
+        """defects for all intervals: (K-1, nx)"""
+        return (np.einsum("kij,kj->ki", self.Jn, W[1:]) + np.einsum("kij,kj->ki", self.Jp, W[:-1])
+                + self.Js * sig - self.p.z_bar.T)
+
+    def solve(self):
+        p, K, nx, nu, ns, d = self.p, self.K, self.nx, self.nu, self.ns, self.d
+        m = p.model
+        Ex, Eu = self.Ex, self.Eu
+        nEx, nEu = len(Ex), len(Eu)
+        free = np.ones(K, bool); free[0] = free[K - 1] = False
+        Wref = np.vstack([p.X_ref, p.U_ref]).T.copy()          # (K, ns)
+        r_tr = p.tr_radius
+        # ---- initial point -------------------------------------------------------------------
+        W = Wref.copy()
+        W[0, :nx] = m.x_init; W[K - 1, :nx] = m.x_final; W[0, nx:] = 0.0; W[K - 1, nx:] = 0.0
+        dlt = min(1e-2 * (self.hi_p - self.lo_p), r_tr / (16.0 * ns))
+        W[1:-1, :d] = np.clip(W[1:-1, :d], self.lo_p + dlt, self.hi_p - dlt)
+        if not self.ball:
+            dv = min(1e-2 * m.v_max, r_tr / (16.0 * ns)); dw = min(1e-2 * 2 * m.w_max, r_tr / (16.0 * ns))
+            W[1:-1, nx] = np.clip(W[1:-1, nx], dv, m.v_max - dv)
+            W[1:-1, nx + 1] = np.clip(W[1:-1, nx + 1], -m.w_max + dw, m.w_max - dw)
+        else:
+            nrm = np.linalg.norm(W[1:-1, nx:], axis=1)
+            sc = np.minimum(1.0, 0.99 * m.v_max / np.maximum(nrm, 1e-300))
+            W[1:-1, nx:] *= sc[:, None]
+        sig = max(p.sigma_ref, min(1e-2, r_tr / 16.0))
+        nuv = self._nu(W, sig)
+        t_nu = np.abs(nuv).sum(axis=1).max() * 1.1 + 1.0
+        t_x = np.abs(W[:, :nx] - Wref[:, :nx]).sum(axis=1).max() + r_tr / 4
+        t_u = np.abs(W[:, nx:] - Wref[:, nx:]).sum(axis=1).max() + r_tr / 4
+        mu0 = self.mu0
+
+        def plain_slacks(W, sig, t_nu, t_x, t_u):
+            """h - G z for every plain row family (positive = satisfied)."""
+            nuv = self._nu(W, sig)
+            sN = t_nu - nuv @ Ex.T                                   # (K-1, 8)
+            sX = t_x - (W[:, :nx] - Wref[:, :nx]) @ Ex.T             # (K, 8)
+            sU = t_u - (W[:, nx:] - Wref[:, nx:]) @ Eu.T             # (K, nEu)
+            sG = np.array([r_tr - t_x - t_u - (sig - p.sigma_ref), r_tr - t_x - t_u + (sig - p.sigma_ref), sig])
+            sP = np.concatenate([self.hi_p - W[:, :d], W[:, :d] - self.lo_p], axis=1)   # (K, 2d)
+            if not self.ball:
+                sV = np.stack([m.v_max - W[:, nx], W[:, nx], m.w_max - W[:, nx + 1], m.w_max + W[:, nx + 1]], axis=1)
+            else:
+                sV = (0.5 * (m.v_max ** 2 - (W[:, nx:] ** 2).sum(axis=1)))[:, None]
+            return sN, sX, sU, sG, sP, sV
+
+        sN, sX, sU, sG, sP, sV = [np.maximum(a, 1e-8) for a in plain_slacks(W, sig, t_nu, t_x, t_u)]
+        lN, lX, lU, lG, lP, lV = mu0 / sN, mu0 / sX, mu0 / sU, mu0 / sG, mu0 / sP, mu0 / sV
+        # hinge rows (free stages only)
+        P_ = W[:, :d].T                                               # (d, K)
+        viol = self.hb - np.einsum("hdk,dk->hk", self.ha, P_)         # b - a.p  (nh, K)
+        hw = self.hw[:, None]
+        disc = np.sqrt((hw * viol) ** 2 + 4 * mu0 ** 2)
+        num = np.where(viol >= 0, hw * viol + disc, 4 * mu0 ** 2 / np.maximum(disc - hw * viol, 1e-300))
+        xi = (num + 2 * mu0) / (2 * hw)
+        s2 = xi.copy(); s1 = xi - viol
+        l1, l2 = mu0 / s1, mu0 / s2
+        hfree = np.broadcast_to(free[None, :], xi.shape)
+
+        n_rows = (K - 1) * nEx + K * nEx + K * nEu + 3 + (K - 2) * (2 * d + sV.shape[1]) + 2 * self.nh * (K - 2)
+        status, it = 1, 0
+        for it in range(self.max_iter):
+            # ---- residuals ---------------------------------------------------------------------
+            gN, gX, gU, gG, gP, gV = plain_slacks(W, sig, t_nu, t_x, t_u)     # h - Gz
+            rN, rX, rU, rG, rP, rV = sN - gN, sX - gX, sU - gU, sG - gG, sP - gP, sV - gV   # r_p = Gz + s - h
+            viol = self.hb - np.einsum("hdk,dk->hk", self.ha, W[:, :d].T)
+            r1 = viol - xi + s1            # -a.p - xi + s1 + b
+            r2 = -xi + s2
+            fm = free[:, None]
+            comp = (sN * lN).sum() + (sX * lX).sum() + (sU * lU).sum() + (sG * lG).sum() + ((sP * lP) * fm).sum() \
+                + ((sV * lV) * fm).sum() + ((s1 * l1 + s2 * l2) * hfree).sum()
+            mu = comp / n_rows
+            rp_inf = max(np.abs(rN).max(), np.abs(rX).max(), np.abs(rU).max(), np.abs(rG).max(),
+                         np.abs(rP[free]).max(), np.abs(rV[free]).max(),
+                         np.abs(r1[:, free]).max() if self.nh else 0.0, np.abs(r2[:, free]).max() if self.nh else 0.0)
+            # stationarity  q + P z + G' lam   (built through the same scatter as the rhs)
+            rdW, rdg = self._scatter(lN, lX, lU, lG, lP, lV, l1, W, free)
+            rdW[:, :d] += self.qrho * W[:, :d] + self.qlin.T
+            rdg[0] += self.c_sig; rdg[1] += self.c_tnu
+            rxi = self.hw[:, None] - l1 - l2
+            rd_inf = max(np.abs(rdW[free]).max(), np.abs(rdg).max(), np.abs(rxi[:, free]).max() if self.nh else 0.0)
+            obj = self.c_sig * sig + self.c_tnu * t_nu + (self.hw[:, None] * xi * hfree).sum() \
+                + 0.5 * self.qrho * (W[:, :d] ** 2).sum() + (self.qlin.T * W[:, :d]).sum()
+            if self.verbose:
+                print(f"{it:3d} mu={mu:.2e} rp={rp_inf:.2e} rd={rd_inf:.2e} obj={obj / self.cs:.8e}")
+            if comp <= self.eps_gap * max(abs(obj), 1e-3) and rp_inf <= self.eps_feas and rd_inf <= 1e-6:
+                status = 0
+                break
+            if not np.isfinite(mu):
+                status = 2
+                break
+            # ---- Newton matrix -------------------------------------------------------------------
+            wN, wX, wU, wG, wP, wV = lN / sN, lX / sX, lU / sU, lG / sG, lP / sP, lV / sV
+            w1, w2 = l1 / s1, l2 / s2
+            weff = w1 * w2 / (w1 + w2)
+            fac = self._factor(wN, wX, wU, wG, wP, wV, lV, weff, W, free)
+
+            def newton(sigmu, cN, cX, cU, cG, cP, cV, c1, c2):
+                """One solve with complementarity targets: tau = (sigmu - c + lam*r_p)/s."""
+                tN = (sigmu - cN + lN * rN) / sN; tX = (sigmu - cX + lX * rX) / sX; tU = (sigmu - cU + lU * rU) / sU
+                tG = (sigmu - cG + lG * rG) / sG; tP = (sigmu - cP + lP * rP) / sP; tV = (sigmu - cV + lV * rV) / sV
+                t1 = (sigmu - c1 + l1 * r1) / s1; t2 = (sigmu - c2 + l2 * r2) / s2
+                rhs_xi = -self.hw[:, None] + t1 + t2
+                # rhs_z = -(Pz+q) - G'tau ; hinge part: + a*(t1 - w1*rhs_xi/(w1+w2))
+                th = t1 - w1 * rhs_xi / (w1 + w2)
+                bW, bg = self._scatter(tN, tX, tU, tG, tP, tV, th, W, free)
+                bW[:, :d] += self.qrho * W[:, :d] + self.qlin.T
+                bg[0] += self.c_sig; bg[1] += self.c_tnu
+                bW, bg = -bW, -bg
+                bW[~free] = 0.0
+                dW, dg = self._solve(fac, bW, bg)
+                # recover row steps
+                dnu = (np.einsum("kij,kj->ki", self.Jn, dW[1:]) + np.einsum("kij,kj->ki", self.Jp, dW[:-1]) + self.Js * dg[0])
+                dsN = -rN - (dnu @ Ex.T - dg[1]); dsX = -rX - (dW[:, :nx] @ Ex.T - dg[2]); dsU = -rU - (dW[:, nx:] @ Eu.T - dg[3])
+                dsG = -rG - np.array([dg[2] + dg[3] + dg[0], dg[2] + dg[3] - dg[0], -dg[0]])
+                dsP = -rP - np.concatenate([dW[:, :d], -dW[:, :d]], axis=1)
+                if not self.ball:
+                    dsV = -rV - np.stack([dW[:, nx], -dW[:, nx], dW[:, nx + 1], -dW[:, nx + 1]], axis=1)
+                else:
+                    dsV = -rV - (W[:, nx:] * dW[:, nx:]).sum(axis=1)[:, None]
+                adp = np.einsum("hdk,dk->hk", self.ha, dW[:, :d].T)
+                dxi = (rhs_xi - w1 * adp) / (w1 + w2)
+                ds1 = -r1 + adp + dxi; ds2 = -r2 + dxi
+                dl = lambda l, s, c, ds: -l + (sigmu - c) / s - (l / s) * ds      # noqa: E731
+                return (dW, dg, dxi, (dsN, dsX, dsU, dsG, dsP, dsV, ds1, ds2),
+                        (dl(lN, sN, cN, dsN), dl(lX, sX, cX, dsX), dl(lU, sU, cU, dsU), dl(lG, sG, cG, dsG),
+                         dl(lP, sP, cP, dsP), dl(lV, sV, cV, dsV), dl(l1, s1, c1, ds1), dl(l2, s2, c2, ds2)))
+
+            S = (sN, sX, sU, sG, sP, sV, s1, s2); L = (lN, lX, lU, lG, lP, lV, l1, l2)
+            masks = (None, None, None, None, fm, fm, hfree, hfree)
+
+            def maxstep(vals, dvals):
+                a = 1.0
+                for v, dv, mk in zip(vals, dvals, masks):
+                    neg = dv < 0
+                    if mk is not None:
+                        neg = neg & np.broadcast_to(mk, dv.shape)
+                    if neg.any():
+                        a = min(a, float((-v[neg] / dv[neg]).min()))
+                return a
+
+            z0 = 0.0
+            dW, dg, dxi, dS, dL = newton(0.0, z0, z0, z0, z0, z0, z0, z0, z0)
+            ap, ad = maxstep(S, dS), maxstep(L, dL)
+            comp_aff = 0.0
+            for v, dv, l, dl_, mk in zip(S, dS, L, dL, masks):
+                t = (v + ap * dv) * (l + ad * dl_)
+                comp_aff += (t * mk).sum() if mk is not None else t.sum()
+            sg = (comp_aff / comp) ** 3
+            cc = [dv * dl_ for dv, dl_ in zip(dS, dL)]
+            dW, dg, dxi, dS, dL = newton(sg * mu, *cc)
+            ap, ad = maxstep(S, dS), maxstep(L, dL)
+            if self.qrho > 0 or self.ball:
+                ap = ad = min(ap, ad)
+            ap, ad = min(1.0, 0.99 * ap), min(1.0, 0.99 * ad)
+            W = W + ap * dW; sig += ap * dg[0]; t_nu += ap * dg[1]; t_x += ap * dg[2]; t_u += ap * dg[3]
+            xi = xi + ap * dxi
+            sN, sX, sU, sG, sP, sV, s1, s2 = [v + ap * dv for v, dv in zip(S, dS)]
+            lN, lX, lU, lG, lP, lV, l1, l2 = [l + ad * dl_ for l, dl_ in zip(L, dL)]
+        X = W[:, :nx].T.copy(); U = W[:, nx:].T.copy()
+        return {"X": X, "U": U, "sigma": float(sig), "iters": it, "status": status, "t": (t_nu, t_x, t_u)}
+
+    # ------------------------------------------------------------------------------------------
+    def _scatter(self, vN, vX, vU, vG, vP, vV, vH, W, free):
+        """G' v for row-wise values v (per family); hinge rows contribute -a * vH on positions.
+        Returns (K, ns) stage part and (4,) global part."""
+        K, nx, d = self.K, self.nx, self.d
+        Ex, Eu = self.Ex, self.Eu
+        outW = np.zeros((K, self.ns)); outg = np.zeros(4)
+        eN = vN @ Ex                                  # (K-1, nx): sum_e v_e e
+        outW[:-1] += np.einsum("ki,kij->kj", eN, self.Jp)
+        outW[1:] += np.einsum("ki,kij->kj", eN, self.Jn)
+        outg[0] += (eN * self.Js).sum(); outg[1] -= vN.sum()
+        outW[:, :nx] += vX @ Ex; outg[2] -= vX.sum()
+        outW[:, nx:] += vU @ Eu; outg[3] -= vU.sum()
+        outg[0] += vG[0] - vG[1] - vG[2]; outg[2] += vG[0] + vG[1]; outg[3] += vG[0] + vG[1]
+        fm = free[:, None]
+        vPm = vP * fm
+        outW[:, :d] += vPm[:, :d] - vPm[:, d:]
+        vVm = vV * fm
+        if not self.ball:
+            outW[:, nx] += vVm[:, 0] - vVm[:, 1]; outW[:, nx + 1] += vVm[:, 2] - vVm[:, 3]
+        else:
+            outW[:, nx:] += vVm[:, :1] * W[:, nx:]
+        if self.nh:
+            outW[:, :d] -= np.einsum("hdk,hk->kd", self.ha, vH * free[None, :])
+        return outW, outg
+
+    def _factor(self, wN, wX, wU, wG, wP, wV, lV, weff, W, free):
+        """Assemble H = P + G'WG as block tridiagonal (D_k, E_k = H[k+1,k]) + 4 border columns, then
+        block-Cholesky it.  Fixed stages (0, K-1) are replaced by identity rows/cols."""
+        K, nx, nu, ns, d = self.K, self.nx, self.nu, self.ns, self.d
+        Ex, Eu = self.Ex, self.Eu
+        D = np.zeros((K, ns, ns)); E = np.zeros((K - 1, ns, ns)); Bd = np.zeros((K, ns, 4)); Gg = np.zeros((4, 4))
+        MN = np.einsum("ke,ei,ej->kij", wN, Ex, Ex)          # (K-1, nx, nx)
+        mN = wN @ Ex                                         # (K-1, nx)
+        sNw = wN.sum(axis=1)
+        D[:-1] += np.einsum("kia,kij,kjb->kab", self.Jp, MN, self.Jp)
+        D[1:] += np.einsum("kia,kij,kjb->kab", self.Jn, MN, self.Jn)
+        E += np.einsum("kia,kij,kjb->kab", self.Jn, MN, self.Jp)
+        MJs = np.einsum("kij,kj->ki", MN, self.Js)           # (K-1, nx)
+        Bd[:-1, :, 0] += np.einsum("kia,ki->ka", self.Jp, MJs); Bd[1:, :, 0] += np.einsum("kia,ki->ka", self.Jn, MJs)
+        Bd[:-1, :, 1] -= np.einsum("kia,ki->ka", self.Jp, mN); Bd[1:, :, 1] -= np.einsum("kia,ki->ka", self.Jn, mN)
+        Gg[0, 0] += (self.Js * MJs).sum(); Gg[0, 1] -= (mN * self.Js).sum(); Gg[1, 1] += sNw.sum()
+        MX = np.einsum("ke,ei,ej->kij", wX, Ex, Ex); D[:, :nx, :nx] += MX
+        Bd[:, :nx, 2] -= wX @ Ex; Gg[2, 2] += wX.sum()
+        MU = np.einsum("ke,ei,ej->kij", wU, Eu, Eu); D[:, nx:, nx:] += MU
+        Bd[:, nx:, 3] -= wU @ Eu; Gg[3, 3] += wU.sum()
+        gG = np.array([[1.0, 0, 1, 1], [-1.0, 0, 1, 1], [-1.0, 0, 0, 0]])
+        Gg += np.einsum("r,ri,rj->ij", wG, gG, gG)
+        Gg[1, 0] = Gg[0, 1]
+        fm = free.astype(float)
+        for i in range(d):
+            D[:, i, i] += (wP[:, i] + wP[:, d + i]) * fm + self.qrho
+        if not self.ball:
+            D[:, nx, nx] += (wV[:, 0] + wV[:, 1]) * fm; D[:, nx + 1, nx + 1] += (wV[:, 2] + wV[:, 3]) * fm
+        else:
+            Uv = W[:, nx:]
+            D[:, nx:, nx:] += (wV[:, 0] * fm)[:, None, None] * np.einsum("ki,kj->kij", Uv, Uv)
+            for i in range(nu):
+                D[:, nx + i, nx + i] += lV[:, 0] * fm
+        if self.nh:
+            D[:, :d, :d] += np.einsum("hk,hik,hjk->kij", weff * fm[None, :], self.ha, self.ha)
+        # fixed stages -> identity
+        for k in (0, K - 1):
+            D[k] = np.eye(ns); Bd[k] = 0.0
+        E[0] = 0.0; E[K - 2] = 0.0
+        # block Cholesky
+        Lk = np.zeros((K, ns, ns)); Li = np.zeros((K, ns, ns)); Lo = np.zeros((K - 1, ns, ns))
+        ok = True
+        for k in range(K):
+            Dk = D[k] - (Lo[k - 1] @ Lo[k - 1].T if k > 0 else 0.0)
+            Dk = Dk + 1e-13 * np.trace(Dk) / ns * np.eye(ns)
+            try:
+                Lk[k] = np.linalg.cholesky(Dk)
+            except np.linalg.LinAlgError:
+                ok = False
+                Lk[k] = np.linalg.cholesky(Dk + 1e-8 * np.trace(np.abs(Dk)) * np.eye(ns))
+            Li[k] = np.linalg.inv(Lk[k])
+            if k < K - 1:
+                Lo[k] = E[k] @ Li[k].T
+        fac = {"Li": Li, "Lo": Lo, "Bd": Bd, "Gg": Gg, "ok": ok}
+        # Y = T^-1 B' (4 rhs) and the Schur complement
+        Y = self._tsolve(fac, Bd)
+        fac["Y"] = Y
+        fac["S"] = Gg - np.einsum("kia,kib->ab", Bd, Y)
+        return fac
+
+    def _tsolve(self, fac, R):
+        """Solve T V = R for R (K, ns, nrhs) with the block-Cholesky factor."""
+        Li, Lo = fac["Li"], fac["Lo"]
+        K = self.K
+        V = np.zeros_like(R)
+        for k in range(K):
+            r = R[k] - (Lo[k - 1] @ V[k - 1] if k > 0 else 0.0)
+            V[k] = Li[k] @ r
+        for k in range(K - 1, -1, -1):
+            r = V[k] - (Lo[k].T @ V[k + 1] if k < K - 1 else 0.0)
+            V[k] = Li[k].T @ r
+        return V
+
+    def _solve(self, fac, bW, bg):
+        v = self._tsolve(fac, bW[:, :, None])[:, :, 0]
+        rg = bg - np.einsum("kia,ki->a", fac["Bd"], v)
+        dg = np.linalg.solve(fac["S"], rg)
+        dW = v - np.einsum("kia,a->ki", fac["Y"], dg)
+        return dW, dg

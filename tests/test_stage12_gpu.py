@@ -34,8 +34,10 @@ def test_foh_golden_unicycle(cuda, golden, tag):
     out = foh.calculate_discretization(X, U, s)
     for nm, arr in zip("ABCSz", out):
         assert rel_err(arr, golden[f"uni_{tag}_tight_{nm}"]) < REL_TOL, nm
-        # vs the reference's default-tolerance odeint output: its own error level
-        assert rel_err(arr, golden[f"uni_{tag}_ref_{nm}"]) < 5e-7, nm
+        # vs the reference's default-tolerance odeint output: bounded by ITS integration error, which is up to
+        # 2.4e-6 of the array scale on these inputs (ref vs tight in the golden file) -- reported, not the gate
+        assert rel_err(arr, golden[f"uni_{tag}_ref_{nm}"]) < 1e-5, nm
+        assert rel_err(arr, golden[f"uni_{tag}_tight_{nm}"]) <= rel_err(golden[f"uni_{tag}_ref_{nm}"], golden[f"uni_{tag}_tight_{nm}"])
     # shapes as asserted by SCvx/tests/test_disc.py:9-27
     assert out[0].shape == (9, 49) and out[1].shape == (6, 49) and out[2].shape == (6, 49)
     assert out[3].shape == (3, 49) and out[4].shape == (3, 49)
@@ -66,7 +68,12 @@ def test_foh_warm_start_iteration0(cuda, golden):
     np.testing.assert_array_equal(X, golden["uni_init_X"])
     out = FirstOrderHold(m, 50).calculate_discretization(X, U, 1.0)
     for nm, arr in zip("ABCSz", out):
-        assert rel_err(arr, golden[f"uni_init_ref_{nm}"]) < 1e-8, nm
+        assert rel_err(arr, golden[f"uni_init_ref_{nm}"]) < 1e-6, nm     # the reference's own odeint error (~3e-8 here)
+    # U = 0 => f = 0, A = 0: exact values Phi = I, B_bar = C_bar = sigma*dt/2 * B(theta=0), S_bar = z_bar = 0
+    dt = 1.0 / 49
+    np.testing.assert_allclose(out[1][:, 7], [dt / 2, 0, 0, 0, 0, dt / 2], atol=1e-15)
+    np.testing.assert_allclose(out[2][:, 7], [dt / 2, 0, 0, 0, 0, dt / 2], atol=1e-15)
+    assert np.abs(out[3]).max() == 0.0 and np.abs(out[4]).max() == 0.0
 
 
 def test_nonlinear_integrators(cuda, golden):
