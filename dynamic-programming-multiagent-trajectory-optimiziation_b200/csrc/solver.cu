@@ -1,8 +1,1449 @@
-// solver.cu -- stage 3 (placeholder while the IPM kernel is being brought up)
+// solver.cu -- stage 3: the convex sub-problem of SCvx, batched, fp64, sm_100a.
+//
+// Replaces SCProblem.solve (SCvx/optimization/sc_problem.py:15-105; model rows unicycle_model.py:85-115,
+// single_integrator_model.py:79-128) and AgentSolver.setup+solve (agent_solver.py:43-117): where the
+// reference builds a cvxpy graph and calls ECOS, this kernel runs a structure-exploiting primal-dual
+// interior-point method (Mehrotra predictor-corrector), ONE THREAD BLOCK PER AGENT.
+//
+// Formulation (oracle/ipm_struct.py is the line-by-line CPU twin of this file):
+//   z = (w_0..w_{K-1}; sigma, t_nu, t_x, t_u),  w_k = (x_k, u_k);  w_0, w_{K-1} fixed by the boundary conditions
+//   min  c_s [ w_nu t_nu + w_sigma sigma + sum_h w_h max(0, b_hk - a_hk.p_k) + rho/2 |P|^2 + <lin, P> ]
+//   s.t. e.nu_k(z) <= t_nu, e.(x_k - xref_k) <= t_x, e.(u_k - uref_k) <= t_u   for ALL sign patterns e   (L1 epigraphs
+//        without auxiliary variables: |v|_1 <= t  <=>  e.v <= t for every e in {+-1}^n),
+//        t_x + t_u +- (sigma - sigma_ref) <= r, sigma >= 0, position box, input box (unicycle) or
+//        1/2(|u_k|^2 - v_max^2) <= 0 (single integrator).
+//   Each hinge term carries a private slack xi (rows -a.p - xi <= -b, -xi <= 0) that is eliminated analytically
+//   from the Newton system, so the KKT matrix is block tridiagonal (n_s x n_s blocks, n_s = n_x + n_u) with a
+//   4-column border (sigma, t_nu, t_x, t_u) whatever the number of obstacles / neighbours.
+//
+// Per IPM iteration: row passes are data-parallel over stages (thread k owns stage k and interval k);
+// the block-Cholesky factorisation and the two substitution sweeps run on warp 0 with the whole factor
+// resident in shared memory; reductions use warp shuffles.  Row state (s, lambda) lives in a global workspace
+// laid out [row][k] so that every access is coalesced over k.
 #include "common.cuh"
+
+namespace scvx {
+
+constexpr int SOLVER_MAX_THREADS = 256;
+
+// ---- small helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide reduction of NV values per thread; op: 0 = sum, 1 = min, 2 = max (per slot).  Result in red[0..NV).
+template <int NV>
+__device__ __forceinline__ void block_reduce(double* vals, const int* ops, double* red /* [8][NV] + [NV] */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    double v = vals[i];
+    v = (ops[i] == 0) ? wsum(v) : (ops[i] == 1 ? wmin(v) : wmax(v));
+    if (lane == 0) red[(wid + 1) * NV + i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    const int i = threadIdx.x;
+    double v = red[NV + i];
+    for (int w = 1; w < nw; ++w) {
+      const double o = red[(w + 1) * NV + i];
+      v = (ops[i] == 0) ? v + o : (ops[i] == 1 ? fmin(v, o) : fmax(v, o));
+    }
+    red[i] = v;
+  }
+  __syncthreads();
+}
+
+template <class M>
+struct Dims {
+  static constexpr int NX = M::NX, NU = M::NU, D = M::D, NS = NX + NU;
+  static constexpr bool BALL = (NU == 3);                 // single integrator: ||u||_2 <= v_max
+  static constexpr int NEX = 1 << NX, NEU = 1 << NU;
+  static constexpr int NV = BALL ? 1 : 4;                 // input rows per stage
+  static constexpr int NPLAIN = NEX + NEX + NEU + 2 * D + NV;
+  static constexpr int R_NU = 0, R_X = NEX, R_U = 2 * NEX, R_P = 2 * NEX + NEU, R_V = R_P + 2 * D;
+  static constexpr int NJ = NX * NX + 2 * NX * NU + 2 * NX;    // jacobian doubles per interval (27 / 33, odd)
+  static constexpr int NSP = NS | 1;                      // padded stage stride (odd)
+  static constexpr int SD = (NS * NS) | 1;                // padded block stride (odd)
+  static constexpr int SR = (NS * 4) | 1;                 // padded border stride (odd)
+  static constexpr int STG = 17;                          // per-interval staging doubles (16 used)
+  static constexpr int PER_STAGE = 4 * NSP + NJ + 2 * SD + SR + STG;
+  static constexpr int SMALL = 64 + 9 * 24;               // globals + reduction scratch
+};
+
+__device__ __forceinline__ double sgn(int e, int i) { return ((e >> i) & 1) ? -1.0 : 1.0; }
+
+struct AgentPtrs {
+  double *sP, *lP;                     // [NPLAIN][K]
+  double *xi, *s1, *s2, *l1, *l2;      // [NH][K]
+};
+
+// ---- per-stage linear forms ----------------------------------------------------------------------
+// nu-like combination for interval k: Jn w_{k+1} + Jp w_k + Js g_sigma (- zbar if AFFINE)
+template <class Dm, bool AFFINE>
+__device__ __forceinline__ void nu_form(const double* jac, const double* wk, const double* wk1, double gsig, double* out) {
+  constexpr int NX = Dm::NX, NU = Dm::NU;
+  const double* A = jac;
+  const double* B = jac + NX * NX;
+  const double* C = B + NX * NU;
+  const double* S = C + NX * NU;
+  const double* Z = S + NX;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+    double v = wk1[i] - S[i] * gsig;
+    if (AFFINE) v -= Z[i];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) v -= A[j * NX + i] * wk[j];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) v -= B[j * NX + i] * wk[NX + j] + C[j * NX + i] * wk1[NX + j];
+    out[i] = v;
+  }
+}
+// Jp' v (NS) and Jn' v (NS) for a 3-vector v;  Jp = [-A, -B], Jn = [I, -C]
+template <class Dm>
+__device__ __forceinline__ void JpT(const double* jac, const double* v, double* out) {
+  constexpr int NX = Dm::NX, NU = Dm::NU;
+  const double* A = jac;
+  const double* B = jac + NX * NX;
+#pragma unroll
+  for (int j = 0; j < NX; ++j) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) a -= A[j * NX + i] * v[i];
+    out[j] = a;
+  }
+#pragma unroll
+  for (int j = 0; j < NU; ++j) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) a -= B[j * NX + i] * v[i];
+    out[NX + j] = a;
+  }
+}
+template <class Dm>
+__device__ __forceinline__ void JnT(const double* jac, const double* v, double* out) {
+  constexpr int NX = Dm::NX, NU = Dm::NU;
+  const double* C = jac + NX * NX + NX * NU;
+#pragma unroll
+  for (int j = 0; j < NX; ++j) out[j] = v[j];
+#pragma unroll
+  for (int j = 0; j < NU; ++j) {
+    double a = 0.0;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) a -= C[j * NX + i] * v[i];
+    out[NX + j] = a;
+  }
+}
+// dense Jp / Jn into registers [NX][NS]
+template <class Dm>
+__device__ __forceinline__ void load_Jp(const double* jac, double (*J)[Dm::NS]) {
+  constexpr int NX = Dm::NX, NU = Dm::NU;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) J[i][j] = -jac[j * NX + i];
+#pragma unroll
+    for (int j = 0; j < NU; ++j) J[i][NX + j] = -jac[NX * NX + j * NX + i];
+  }
+}
+template <class Dm>
+__device__ __forceinline__ void load_Jn(const double* jac, double (*J)[Dm::NS]) {
+  constexpr int NX = Dm::NX, NU = Dm::NU;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) J[i][j] = (i == j) ? 1.0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < NU; ++j) J[i][NX + j] = -jac[NX * NX + NX * NU + j * NX + i];
+  }
+}
+
+// Everything the kernel needs about one agent's problem, resident in registers / constant per thread.
+struct Scal {
+  double sig_ref, r_tr, pos_lo, pos_hi, v_max, w_max;
+  double c_sig, c_tnu, cs, qrho, hw_obs, hw_col;
+};
+
+// ---- the kernel -----------------------------------------------------------------------------------
+template <class M>
+__global__ void __launch_bounds__(SOLVER_MAX_THREADS, 1)
+ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
+  using Dm = Dims<M>;
+  constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
+  constexpr int NSP = Dm::NSP, SD = Dm::SD, SR = Dm::SR, NJ = Dm::NJ, STG = Dm::STG, NPLAIN = Dm::NPLAIN;
+  constexpr bool BALL = Dm::BALL;
+  const int K = a.K, agent = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int Mobs = a.M, NH = a.M + a.n_nbr;
+
+  extern __shared__ __align__(16) double smem[];
+  double* W = smem;                     // [K][NSP] current stage variables
+  double* Wr = W + (size_t)K * NSP;     // [K][NSP] trust-region centre
+  double* dWa = Wr + (size_t)K * NSP;   // [K][NSP] affine (predictor) direction
+  double* dW = dWa + (size_t)K * NSP;   // [K][NSP] rhs / solution of the current solve
+  double* JAC = dW + (size_t)K * NSP;   // [K][NJ]
+  double* Dk = JAC + (size_t)K * NJ;    // [K][SD]   diagonal blocks -> Li (inverse Cholesky factor)
+  double* Ek = Dk + (size_t)K * SD;     // [K][SD]   sub-diagonal blocks H[k+1,k] -> Lo
+  double* Rb = Ek + (size_t)K * SD;     // [K][SR]   border columns Bd -> Y = T^-1 Bd     layout [c*NS + i]
+  double* ST = Rb + (size_t)K * SR;     // [K][STG]  per-interval staging
+  double* gl = ST + (size_t)K * STG;    // [64] globals
+  double* red = gl + 64;                // [9][24] reduction scratch
+  // globals: gl[0..3] = sigma, t_nu, t_x, t_u ; gl[4..7] = dg_aff ; gl[8..11] = dg ; gl[12..14] sG ; gl[15..17] lG ;
+  // gl[18..33] = Gg/S 4x4 ; gl[34..37] = bg ; gl[40] flag ; gl[41] alpha_p ; gl[42] alpha_d ; gl[43] sigmu ; gl[44] mu
+  // gl[45] comp ; gl[46..49] Y'b scratch
+
+  // ---- per-agent scalars & pointers --------------------------------------------------------------
+  Scal sc;
+  sc.sig_ref = a.sigma_ref[agent]; sc.r_tr = a.tr_radius[agent];
+  sc.pos_lo = a.pos_lo[agent]; sc.pos_hi = a.pos_hi[agent];
+  sc.v_max = a.v_max[agent]; sc.w_max = a.w_max ? a.w_max[agent] : 0.0;
+  sc.cs = 1.0 / fmax(fmax(a.weight_nu, a.weight_sigma), 1e-300);
+  sc.c_sig = a.weight_sigma * sc.cs; sc.c_tnu = a.weight_nu * sc.cs;
+  sc.qrho = a.quad_rho ? a.quad_rho[agent] * sc.cs : 0.0;
+  sc.hw_obs = a.weight_slack * sc.cs; sc.hw_col = a.weight_col * sc.cs;
+  const double* qlin = a.lin_p ? a.lin_p + (size_t)agent * D * K : nullptr;
+  const double* obs_a = a.obs_a ? a.obs_a + (size_t)agent * Mobs * D * K : nullptr;
+  const double* obs_b = a.obs_b ? a.obs_b + (size_t)agent * Mobs * K : nullptr;
+  const double* col_a = a.col_a ? a.col_a + (size_t)agent * a.n_nbr * D * K : nullptr;
+  const double* col_b = a.col_b ? a.col_b + (size_t)agent * a.n_nbr * K : nullptr;
+  const unsigned char* col_mask = a.col_mask ? a.col_mask + (size_t)agent * a.n_nbr : nullptr;
+  const bool coupled = (sc.qrho > 0.0) || BALL;          // common primal/dual step length
+
+  AgentPtrs ws;
+  {
+    double* base = (double*)a.workspace + (size_t)agent * ((size_t)K * (2 * NPLAIN + 5 * NH));
+    ws.sP = base; ws.lP = ws.sP + (size_t)NPLAIN * K;
+    ws.xi = ws.lP + (size_t)NPLAIN * K; ws.s1 = ws.xi + (size_t)NH * K; ws.s2 = ws.s1 + (size_t)NH * K;
+    ws.l1 = ws.s2 + (size_t)NH * K; ws.l2 = ws.l1 + (size_t)NH * K;
+  }
+  auto hinge_a = [&](int h, int c, int k) -> double {
+    return (h < Mobs) ? obs_a[((size_t)h * D + c) * K + k] : col_a[((size_t)(h - Mobs) * D + c) * K + k];
+  };
+  auto hinge_b = [&](int h, int k) -> double {
+    return (h < Mobs) ? obs_b[(size_t)h * K + k] : col_b[(size_t)(h - Mobs) * K + k];
+  };
+  auto hinge_on = [&](int h) -> bool { return (h < Mobs) || !col_mask || col_mask[h - Mobs]; };
+  auto hinge_w = [&](int h) -> double { return (h < Mobs) ? sc.hw_obs : sc.hw_col; };
+
+  // ---- load problem data into shared memory ---------------------------------------------------------
+  {
+    const double* Xr = a.X_ref + (size_t)agent * NX * K;
+    const double* Ur = a.U_ref + (size_t)agent * NU * K;
+    for (int k = tid; k < K; k += nthr) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Wr[k * NSP + i] = Xr[(size_t)i * K + k];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) Wr[k * NSP + NX + j] = Ur[(size_t)j * K + k];
+    }
+    const int Km1 = K - 1;
+    const double* Ab = a.A_bar + (size_t)agent * NX * NX * Km1;
+    const double* Bb = a.B_bar + (size_t)agent * NX * NU * Km1;
+    const double* Cb = a.C_bar + (size_t)agent * NX * NU * Km1;
+    const double* Sb = a.S_bar + (size_t)agent * NX * Km1;
+    const double* Zb = a.z_bar + (size_t)agent * NX * Km1;
+    for (int k = tid; k < Km1; k += nthr) {
+      double* j = JAC + (size_t)k * NJ;
+#pragma unroll
+      for (int r = 0; r < NX * NX; ++r) j[r] = Ab[(size_t)r * Km1 + k];
+#pragma unroll
+      for (int r = 0; r < NX * NU; ++r) { j[NX * NX + r] = Bb[(size_t)r * Km1 + k]; j[NX * NX + NX * NU + r] = Cb[(size_t)r * Km1 + k]; }
+#pragma unroll
+      for (int r = 0; r < NX; ++r) { j[NX * NX + 2 * NX * NU + r] = Sb[(size_t)r * Km1 + k]; j[NX * NX + 2 * NX * NU + NX + r] = Zb[(size_t)r * Km1 + k]; }
+    }
+  }
+  __syncthreads();
+
+  // ---- initial point (strictly inside the boxes; t's large enough; central complementarity) ----------
+  {
+    const double dlt = fmin(1e-2 * (sc.pos_hi - sc.pos_lo), sc.r_tr / (16.0 * NS));
+    const double dv = fmin(1e-2 * sc.v_max, sc.r_tr / (16.0 * NS));
+    const double dw = fmin(2e-2 * sc.w_max, sc.r_tr / (16.0 * NS));
+    for (int k = tid; k < K; k += nthr) {
+      double* w = W + k * NSP;
+      if (k == 0 || k == K - 1) {
+        const double* xb = (k == 0 ? a.x_init : a.x_final) + (size_t)agent * NX;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) w[i] = xb[i];
+#pragma unroll
+        for (int j = 0; j < NU; ++j) w[NX + j] = 0.0;
+      } else {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) w[i] = Wr[k * NSP + i];
+#pragma unroll
+        for (int i = 0; i < D; ++i) w[i] = fmin(fmax(w[i], sc.pos_lo + dlt), sc.pos_hi - dlt);
+        if (!BALL) {
+          w[NX] = fmin(fmax(w[NX], dv), sc.v_max - dv);
+          w[NX + 1] = fmin(fmax(w[NX + 1], -sc.w_max + dw), sc.w_max - dw);
+        } else {
+          double n2 = 0.0;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
+          const double s = fmin(1.0, 0.99 * sc.v_max / fmax(sqrt(n2), 1e-300));
+#pragma unroll
+          for (int j = 0; j < NU; ++j) w[NX + j] *= s;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { dWa[k * NSP + i] = 0.0; dW[k * NSP + i] = 0.0; }
+    }
+  }
+  __syncthreads();
+  {
+    // t_nu, t_x, t_u from maxima over stages
+    const double sig0 = fmax(sc.sig_ref, fmin(1e-2, sc.r_tr / 16.0));
+    double v[3] = {0.0, 0.0, 0.0};
+    for (int k = tid; k < K; k += nthr) {
+      const double* w = W + k * NSP;
+      if (k < K - 1) {
+        double nu[NX];
+        nu_form<Dm, true>(JAC + (size_t)k * NJ, w, w + NSP, sig0, nu);
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s += fabs(nu[i]);
+        v[0] = fmax(v[0], s);
+      }
+      double sx = 0.0, su = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sx += fabs(w[i] - Wr[k * NSP + i]);
+#pragma unroll
+      for (int j = 0; j < NU; ++j) su += fabs(w[NX + j] - Wr[k * NSP + NX + j]);
+      v[1] = fmax(v[1], sx); v[2] = fmax(v[2], su);
+    }
+    const int ops[3] = {2, 2, 2};
+    block_reduce<3>(v, ops, red);
+    if (tid == 0) {
+      gl[0] = sig0; gl[1] = red[0] * 1.1 + 1.0; gl[2] = red[1] + sc.r_tr * 0.25; gl[3] = red[2] + sc.r_tr * 0.25;
+      const double sG[3] = {sc.r_tr - gl[2] - gl[3] - (sig0 - sc.sig_ref), sc.r_tr - gl[2] - gl[3] + (sig0 - sc.sig_ref), sig0};
+      for (int r = 0; r < 3; ++r) { gl[12 + r] = fmax(sG[r], 1e-8); gl[15 + r] = mu0 / gl[12 + r]; }
+    }
+    __syncthreads();
+  }
+  // row state init
+  for (int k = tid; k < K; k += nthr) {
+    const double* w = W + k * NSP;
+    const double sig = gl[0], tnu = gl[1], tx = gl[2], tu = gl[3];
+    const bool fr = (k > 0 && k < K - 1);
+    if (k < K - 1) {
+      double nu[NX];
+      nu_form<Dm, true>(JAC + (size_t)k * NJ, w, w + NSP, sig, nu);
+#pragma unroll
+      for (int e = 0; e < NEX; ++e) {
+        double f = -tnu;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) f += sgn(e, i) * nu[i];
+        const double s = fmax(-f, 1e-8);
+        ws.sP[(size_t)(Dm::R_NU + e) * K + k] = s; ws.lP[(size_t)(Dm::R_NU + e) * K + k] = mu0 / s;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < NEX; ++e) {
+      double f = -tx;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) f += sgn(e, i) * (w[i] - Wr[k * NSP + i]);
+      const double s = fmax(-f, 1e-8);
+      ws.sP[(size_t)(Dm::R_X + e) * K + k] = s; ws.lP[(size_t)(Dm::R_X + e) * K + k] = mu0 / s;
+    }
+#pragma unroll
+    for (int e = 0; e < NEU; ++e) {
+      double f = -tu;
+#pragma unroll
+      for (int j = 0; j < NU; ++j) f += sgn(e, j) * (w[NX + j] - Wr[k * NSP + NX + j]);
+      const double s = fmax(-f, 1e-8);
+      ws.sP[(size_t)(Dm::R_U + e) * K + k] = s; ws.lP[(size_t)(Dm::R_U + e) * K + k] = mu0 / s;
+    }
+    if (fr) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        double s = fmax(sc.pos_hi - w[i], 1e-8);
+        ws.sP[(size_t)(Dm::R_P + i) * K + k] = s; ws.lP[(size_t)(Dm::R_P + i) * K + k] = mu0 / s;
+        s = fmax(w[i] - sc.pos_lo, 1e-8);
+        ws.sP[(size_t)(Dm::R_P + D + i) * K + k] = s; ws.lP[(size_t)(Dm::R_P + D + i) * K + k] = mu0 / s;
+      }
+      if (!BALL) {
+        const double sv[4] = {sc.v_max - w[NX], w[NX], sc.w_max - w[NX + 1], sc.w_max + w[NX + 1]};
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const double s = fmax(sv[r], 1e-8);
+          ws.sP[(size_t)(Dm::R_V + r) * K + k] = s; ws.lP[(size_t)(Dm::R_V + r) * K + k] = mu0 / s;
+        }
+      } else {
+        double n2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
+        const double s = fmax(0.5 * (sc.v_max * sc.v_max - n2), 1e-8);
+        ws.sP[(size_t)Dm::R_V * K + k] = s; ws.lP[(size_t)Dm::R_V * K + k] = mu0 / s;
+      }
+      for (int h = 0; h < NH; ++h) {
+        if (!hinge_on(h)) continue;
+        double ap = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) ap += hinge_a(h, c, k) * w[c];
+        const double viol = hinge_b(h, k) - ap, hw = hinge_w(h);
+        const double disc = sqrt(hw * viol * hw * viol + 4.0 * mu0 * mu0);
+        const double num = (viol >= 0.0) ? hw * viol + disc : 4.0 * mu0 * mu0 / fmax(disc - hw * viol, 1e-300);
+        const double xi = (num + 2.0 * mu0) / (2.0 * hw);
+        const size_t o = (size_t)h * K + k;
+        ws.xi[o] = xi; ws.s2[o] = xi; ws.s1[o] = xi - viol; ws.l1[o] = mu0 / (xi - viol); ws.l2[o] = mu0 / xi;
+      }
+    }
+  }
+  __syncthreads();
+
+  // number of complementarity pairs
+  int n_active_h = 0;
+  for (int h = 0; h < NH; ++h) n_active_h += hinge_on(h) ? 1 : 0;
+  const double n_rows = (double)(K - 1) * NEX + (double)K * NEX + (double)K * NEU + 3.0 +
+                        (double)(K - 2) * (2 * D + Dm::NV) + 2.0 * n_active_h * (double)(K - 2);
+
+  int status = SCVX_ST_MAXITER, it = 0;
+  const int max_iter = a.max_iter > 0 ? a.max_iter : 60;
+
+  // =================================================================================================
+  // A row pass.  MODE 0: residuals + Newton matrix staging + predictor rhs staging + stationarity staging
+  //              MODE 1: affine step statistics (alpha_p, alpha_d, three sums for mu_aff)
+  //              MODE 2: corrector rhs staging
+  //              MODE 3: final step lengths
+  //              MODE 4: apply the step to the row state
+  // Per-stage results that other threads need go to ST (interval part) and dW / Dk / Rb (own stage).
+  // =================================================================================================
+  for (it = 0; it < max_iter; ++it) {
+    double part[24];
+    // ------------------------------------------------------------------------------------ MODE 0
+#pragma unroll
+    for (int i = 0; i < 24; ++i) part[i] = 0.0;
+    // part: 0 comp, 1 rp_inf, 2 rd_inf(xi), 3 Gg00, 4 Gg01, 5 Gg11, 6 Gg22, 7 Gg33, 8..11 bg(tau), 12..15 rdg(lambda), 16 obj_hinge, 17 obj_quad
+    const double sig = gl[0], tnu = gl[1], tx = gl[2], tu = gl[3];
+    for (int k = tid; k < K; k += nthr) {
+      const double* w = W + k * NSP;
+      const bool fr = (k > 0 && k < K - 1);
+      double* st = ST + (size_t)k * STG;
+      // ---- nu rows of interval k
+      if (k < K - 1) {
+        const double* jac = JAC + (size_t)k * NJ;
+        double nu[NX];
+        nu_form<Dm, true>(jac, w, w + NSP, sig, nu);
+        double Mm[6] = {0, 0, 0, 0, 0, 0}, mv[NX] = {0, 0, 0}, sw = 0.0, et[NX] = {0, 0, 0}, stau = 0.0, el[NX] = {0, 0, 0}, slam = 0.0;
+#pragma unroll
+        for (int e = 0; e < NEX; ++e) {
+          const size_t o = (size_t)(Dm::R_NU + e) * K + k;
+          const double s = ws.sP[o], l = ws.lP[o];
+          double f = -tnu;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) f += sgn(e, i) * nu[i];
+          const double rp = f + s, wgt = l / s, tau = wgt * rp;
+          part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+          sw += wgt; stau += tau; slam += l;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { mv[i] += wgt * sgn(e, i); et[i] += tau * sgn(e, i); el[i] += l * sgn(e, i); }
+          Mm[0] += wgt; Mm[1] += wgt * sgn(e, 0) * sgn(e, 1); Mm[2] += wgt * sgn(e, 0) * sgn(e, 2);
+          Mm[3] += wgt; Mm[4] += wgt * sgn(e, 1) * sgn(e, 2); Mm[5] += wgt;
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) st[i] = Mm[i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { st[6 + i] = mv[i]; st[10 + i] = et[i]; st[13 + i] = el[i]; }
+        st[9] = sw;
+        // global-column contributions of this interval
+        const double* S = jac + NX * NX + 2 * NX * NU;
+        double Js[NX], MJs[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) Js[i] = -S[i];
+        MJs[0] = Mm[0] * Js[0] + Mm[1] * Js[1] + Mm[2] * Js[2];
+        MJs[1] = Mm[1] * Js[0] + Mm[3] * Js[1] + Mm[4] * Js[2];
+        MJs[2] = Mm[2] * Js[0] + Mm[4] * Js[1] + Mm[5] * Js[2];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          part[3] += Js[i] * MJs[i]; part[4] -= mv[i] * Js[i];
+          part[8] += et[i] * Js[i]; part[12] += el[i] * Js[i];
+        }
+        part[5] += sw; part[9] -= stau; part[13] -= slam;
+      }
+      // ---- own-stage accumulators: diag block (sym, full storage), border cols, rhs (tau), stationarity (lambda)
+      double Dl[NS][NS], bt[NS], bl[NS], bx[NX], bu[NU];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        bt[i] = 0.0; bl[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) Dl[i][j] = 0.0;
+      }
+      // x-trust rows
+      {
+        double dx[NX], mvx[NX] = {0, 0, 0}, swx = 0.0, stx = 0.0, slx = 0.0;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dx[i] = w[i] - Wr[k * NSP + i];
+#pragma unroll
+        for (int e = 0; e < NEX; ++e) {
+          const size_t o = (size_t)(Dm::R_X + e) * K + k;
+          const double s = ws.sP[o], l = ws.lP[o];
+          double f = -tx;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) f += sgn(e, i) * dx[i];
+          const double rp = f + s, wgt = l / s, tau = wgt * rp;
+          part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+          swx += wgt; stx += tau; slx += l;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            mvx[i] += wgt * sgn(e, i); bt[i] += tau * sgn(e, i); bl[i] += l * sgn(e, i);
+#pragma unroll
+            for (int j = 0; j < NX; ++j) Dl[i][j] += wgt * sgn(e, i) * sgn(e, j);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) bx[i] = -mvx[i];
+        part[6] += swx; part[10] -= stx; part[14] -= slx;
+      }
+      // u-trust rows
+      {
+        double du[NU], mvu[NU], swu = 0.0, stu = 0.0, slu = 0.0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) { du[j] = w[NX + j] - Wr[k * NSP + NX + j]; mvu[j] = 0.0; }
+#pragma unroll
+        for (int e = 0; e < NEU; ++e) {
+          const size_t o = (size_t)(Dm::R_U + e) * K + k;
+          const double s = ws.sP[o], l = ws.lP[o];
+          double f = -tu;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) f += sgn(e, j) * du[j];
+          const double rp = f + s, wgt = l / s, tau = wgt * rp;
+          part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+          swu += wgt; stu += tau; slu += l;
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            mvu[i] += wgt * sgn(e, i); bt[NX + i] += tau * sgn(e, i); bl[NX + i] += l * sgn(e, i);
+#pragma unroll
+            for (int j = 0; j < NU; ++j) Dl[NX + i][NX + j] += wgt * sgn(e, i) * sgn(e, j);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < NU; ++j) bu[j] = -mvu[j];
+        part[7] += swu; part[11] -= stu; part[15] -= slu;
+      }
+      if (fr) {
+        // position box
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+          size_t o = (size_t)(Dm::R_P + i) * K + k;
+          double s = ws.sP[o], l = ws.lP[o], rp = (w[i] - sc.pos_hi) + s, wgt = l / s;
+          part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+          Dl[i][i] += wgt; bt[i] += wgt * rp; bl[i] += l;
+          o = (size_t)(Dm::R_P + D + i) * K + k;
+          s = ws.sP[o]; l = ws.lP[o]; rp = (sc.pos_lo - w[i]) + s; wgt = l / s;
+          part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+          Dl[i][i] += wgt; bt[i] -= wgt * rp; bl[i] -= l;
+        }
+        if (!BALL) {
+          const double gz[4] = {w[NX] - sc.v_max, -w[NX], w[NX + 1] - sc.w_max, -w[NX + 1] - sc.w_max};
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const size_t o = (size_t)(Dm::R_V + r) * K + k;
+            const double s = ws.sP[o], l = ws.lP[o], rp = gz[r] + s, wgt = l / s;
+            const int c = NX + (r >> 1);
+            const double sg = (r & 1) ? -1.0 : 1.0;
+            part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+            Dl[c][c] += wgt; bt[c] += sg * wgt * rp; bl[c] += sg * l;
+          }
+        } else {
+          const size_t o = (size_t)Dm::R_V * K + k;
+          const double s = ws.sP[o], l = ws.lP[o];
+          double n2 = 0.0;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
+          const double rp = 0.5 * (n2 - sc.v_max * sc.v_max) + s, wgt = l / s;
+          part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            bt[NX + i] += wgt * rp * w[NX + i]; bl[NX + i] += l * w[NX + i];
+            Dl[NX + i][NX + i] += l;
+#pragma unroll
+            for (int j = 0; j < NU; ++j) Dl[NX + i][NX + j] += wgt * w[NX + i] * w[NX + j];
+          }
+        }
+        // hinge rows
+        for (int h = 0; h < NH; ++h) {
+          if (!hinge_on(h)) continue;
+          double av[D], ap = 0.0;
+#pragma unroll
+          for (int c = 0; c < D; ++c) { av[c] = hinge_a(h, c, k); ap += av[c] * w[c]; }
+          const size_t o = (size_t)h * K + k;
+          const double xi = ws.xi[o], s1 = ws.s1[o], s2 = ws.s2[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
+          const double viol = hinge_b(h, k) - ap;
+          const double r1 = viol - xi + s1, r2 = -xi + s2;
+          const double w1 = l1 / s1, w2 = l2 / s2, weff = w1 * w2 / (w1 + w2);
+          const double t1 = w1 * r1, t2 = w2 * r2;
+          const double rhs_xi = -hw + t1 + t2;
+          const double th = t1 - w1 * rhs_xi / (w1 + w2);
+          part[0] += s1 * l1 + s2 * l2;
+          part[1] = fmax(part[1], fmax(fabs(r1), fabs(r2)));
+          part[2] = fmax(part[2], fabs(hw - l1 - l2));
+          part[16] += hw * xi;
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            bt[c] -= av[c] * th; bl[c] -= av[c] * l1;
+#pragma unroll
+            for (int c2 = 0; c2 < D; ++c2) Dl[c][c2] += weff * av[c] * av[c2];
+          }
+        }
+      }
+      // quadratic / linear position terms (enter both the rhs and the stationarity residual)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double ql = qlin ? qlin[(size_t)c * K + k] * sc.cs : 0.0;
+        const double g = sc.qrho * w[c] + ql;
+        bt[c] += g; bl[c] += g;
+        Dl[c][c] += sc.qrho;
+        part[17] += 0.5 * sc.qrho * w[c] * w[c] + ql * w[c];
+      }
+      // write own-stage pieces (interval pieces are added after the barrier)
+      double* dk = Dk + (size_t)k * SD;
+#pragma unroll
+      for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int j = 0; j < NS; ++j) dk[i * NS + j] = Dl[i][j];
+      double* rb = Rb + (size_t)k * SR;
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        rb[0 * NS + i] = 0.0; rb[1 * NS + i] = 0.0;
+        rb[2 * NS + i] = (i < NX) ? bx[i] : 0.0;
+        rb[3 * NS + i] = (i >= NX) ? bu[i - NX] : 0.0;
+        dW[k * NSP + i] = bt[i];
+        dWa[k * NSP + i] = bl[i];     // stationarity accumulator (dWa is free at this point)
+      }
+    }
+    __syncthreads();
+    // ---- second half of the assembly: interval pieces (k-1 via Jn, k via Jp)
+    double rdmax = 0.0;
+    for (int k = tid; k < K; k += nthr) {
+      const bool fr = (k > 0 && k < K - 1);
+      double* dk = Dk + (size_t)k * SD;
+      double* ek = Ek + (size_t)k * SD;
+      double* rb = Rb + (size_t)k * SR;
+      if (!fr) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) { dk[i * NS + j] = (i == j) ? 1.0 : 0.0; ek[i * NS + j] = 0.0; }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) rb[c * NS + i] = 0.0;
+          dW[k * NSP + i] = 0.0;
+        }
+        continue;
+      }
+      double acc_t[NS], acc_l[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { acc_t[i] = dW[k * NSP + i]; acc_l[i] = dWa[k * NSP + i]; }
+      // interval k (this stage is the "previous" node): Jp
+      {
+        const double* jac = JAC + (size_t)k * NJ;
+        const double* st = ST + (size_t)k * STG;
+        double J[NX][NS];
+        load_Jp<Dm>(jac, J);
+        const double M00 = st[0], M01 = st[1], M02 = st[2], M11 = st[3], M12 = st[4], M22 = st[5];
+        double T[NX][NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          T[0][j] = M00 * J[0][j] + M01 * J[1][j] + M02 * J[2][j];
+          T[1][j] = M01 * J[0][j] + M11 * J[1][j] + M12 * J[2][j];
+          T[2][j] = M02 * J[0][j] + M12 * J[1][j] + M22 * J[2][j];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+          for (int j = 0; j < NS; ++j) dk[i * NS + j] += J[0][i] * T[0][j] + J[1][i] * T[1][j] + J[2][i] * T[2][j];
+        // E_k = Jn_k' M_k Jp_k (rows: stage k+1, cols: stage k); zero when stage k+1 is fixed
+        if (k + 1 < K - 1) {
+          double Jn[NX][NS];
+          load_Jn<Dm>(jac, Jn);
+#pragma unroll
+          for (int i = 0; i < NS; ++i)
+#pragma unroll
+            for (int j = 0; j < NS; ++j) ek[i * NS + j] = Jn[0][i] * T[0][j] + Jn[1][i] * T[1][j] + Jn[2][i] * T[2][j];
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS * NS; ++i) ek[i] = 0.0;
+        }
+        const double* S = jac + NX * NX + 2 * NX * NU;
+        double MJs[NX];
+        MJs[0] = -(M00 * S[0] + M01 * S[1] + M02 * S[2]);
+        MJs[1] = -(M01 * S[0] + M11 * S[1] + M12 * S[2]);
+        MJs[2] = -(M02 * S[0] + M12 * S[1] + M22 * S[2]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          rb[0 * NS + i] += J[0][i] * MJs[0] + J[1][i] * MJs[1] + J[2][i] * MJs[2];
+          rb[1 * NS + i] -= J[0][i] * st[6] + J[1][i] * st[7] + J[2][i] * st[8];
+          acc_t[i] += J[0][i] * st[10] + J[1][i] * st[11] + J[2][i] * st[12];
+          acc_l[i] += J[0][i] * st[13] + J[1][i] * st[14] + J[2][i] * st[15];
+        }
+      }
+      // interval k-1 (this stage is the "next" node): Jn
+      {
+        const double* jac = JAC + (size_t)(k - 1) * NJ;
+        const double* st = ST + (size_t)(k - 1) * STG;
+        double J[NX][NS];
+        load_Jn<Dm>(jac, J);
+        const double M00 = st[0], M01 = st[1], M02 = st[2], M11 = st[3], M12 = st[4], M22 = st[5];
+        double T[NX][NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          T[0][j] = M00 * J[0][j] + M01 * J[1][j] + M02 * J[2][j];
+          T[1][j] = M01 * J[0][j] + M11 * J[1][j] + M12 * J[2][j];
+          T[2][j] = M02 * J[0][j] + M12 * J[1][j] + M22 * J[2][j];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+          for (int j = 0; j < NS; ++j) dk[i * NS + j] += J[0][i] * T[0][j] + J[1][i] * T[1][j] + J[2][i] * T[2][j];
+        const double* S = jac + NX * NX + 2 * NX * NU;
+        double MJs[NX];
+        MJs[0] = -(M00 * S[0] + M01 * S[1] + M02 * S[2]);
+        MJs[1] = -(M01 * S[0] + M11 * S[1] + M12 * S[2]);
+        MJs[2] = -(M02 * S[0] + M12 * S[1] + M22 * S[2]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          rb[0 * NS + i] += J[0][i] * MJs[0] + J[1][i] * MJs[1] + J[2][i] * MJs[2];
+          rb[1 * NS + i] -= J[0][i] * st[6] + J[1][i] * st[7] + J[2][i] * st[8];
+          acc_t[i] += J[0][i] * st[10] + J[1][i] * st[11] + J[2][i] * st[12];
+          acc_l[i] += J[0][i] * st[13] + J[1][i] * st[14] + J[2][i] * st[15];
+        }
+      }
+      if (k == 1) {
+        // E_0 couples the fixed stage 0: zero (stage 0 thread wrote zeros already)
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        dW[k * NSP + i] = -acc_t[i];
+        rdmax = fmax(rdmax, fabs(acc_l[i]));
+      }
+    }
+    // E_k for k = 0 is zero (stage 0 fixed) -- written by the !fr branch.  Reduce the partials.
+    part[18] = rdmax;
+    {
+      const int ops[19] = {0, 2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2};
+      block_reduce<19>(part, ops, red);
+    }
+    if (tid == 0) {
+      // global rows
+      const double gz[3] = {tx + tu + (sig - sc.sig_ref) - sc.r_tr, tx + tu - (sig - sc.sig_ref) - sc.r_tr, -sig};
+      const double gG[3][4] = {{1, 0, 1, 1}, {-1, 0, 1, 1}, {-1, 0, 0, 0}};
+      double Gg[4][4] = {{0}}, bg[4], rdg[4];
+      double comp = red[0], rp_inf = red[1];
+      for (int c = 0; c < 4; ++c) { bg[c] = red[8 + c]; rdg[c] = red[12 + c]; }
+      Gg[0][0] = red[3]; Gg[0][1] = Gg[1][0] = red[4]; Gg[1][1] = red[5]; Gg[2][2] = red[6]; Gg[3][3] = red[7];
+      for (int r = 0; r < 3; ++r) {
+        const double s = gl[12 + r], l = gl[15 + r], rp = gz[r] + s, wgt = l / s;
+        comp += s * l; rp_inf = fmax(rp_inf, fabs(rp));
+        gl[50 + r] = rp;
+        for (int i = 0; i < 4; ++i) {
+          bg[i] += gG[r][i] * wgt * rp; rdg[i] += gG[r][i] * l;
+          for (int j = 0; j < 4; ++j) Gg[i][j] += wgt * gG[r][i] * gG[r][j];
+        }
+      }
+      bg[0] += sc.c_sig; bg[1] += sc.c_tnu; rdg[0] += sc.c_sig; rdg[1] += sc.c_tnu;
+      double rd_inf = fmax(red[2], red[18]);
+      for (int c = 0; c < 4; ++c) { rd_inf = fmax(rd_inf, fabs(rdg[c])); gl[34 + c] = -bg[c]; }
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) gl[18 + i * 4 + j] = Gg[i][j];
+      const double obj = sc.c_sig * sig + sc.c_tnu * tnu + red[16] + red[17];
+      const double mu = comp / n_rows;
+      gl[44] = mu; gl[45] = comp;
+      int flag = 0;
+      if (!(mu == mu) || !(rp_inf == rp_inf) || !(rd_inf == rd_inf) || mu > 1e300) flag = 2;
+      else if (comp <= eps_gap * fmax(fabs(obj), 1e-3) && rp_inf <= eps_feas && rd_inf <= 1e-6) flag = 1;
+      gl[40] = (double)flag;
+    }
+    __syncthreads();
+    {
+      const int flag = (int)gl[40];
+      if (flag == 1) { status = SCVX_ST_OPTIMAL; break; }
+      if (flag == 2) { status = SCVX_ST_NUMERICAL; break; }
+    }
+
+    // ------------------------------------------------------------------- factor + predictor solve (warp 0)
+    // Block Cholesky of the tridiagonal part; diagonal blocks are replaced by Li = L^-1 (lower), sub-diagonal
+    // blocks by Lo_k = E_k Li_k'.  Forward substitution of the 4 border columns + the rhs is fused in.
+    if (tid < 32) {
+      const int lane = tid;
+      const int rc = lane / NS, ri = lane % NS;             // (rhs column 0..4, component) role for 5*NS lanes
+      double sacc[10];                                      // Schur accumulators  V'V (10 unique) -- lanes cooperate below
+      (void)sacc;
+      for (int k = 1; k < K - 1; ++k) {
+        double* dk = Dk + (size_t)k * SD;
+        double* ekm = Ek + (size_t)(k - 1) * SD;            // Lo_{k-1}
+        // (a) Dk -= Lo_{k-1} Lo_{k-1}'
+        for (int idx = lane; idx < NS * NS; idx += 32) {
+          const int i = idx / NS, j = idx % NS;
+          double acc = dk[idx];
+#pragma unroll
+          for (int c = 0; c < NS; ++c) acc -= ekm[i * NS + c] * ekm[j * NS + c];
+          dk[idx] = acc;
+        }
+        __syncwarp();
+        // (b,c) every lane: Cholesky + inverse of the NS x NS block in registers
+        double L[NS][NS];
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) L[i][j] = dk[i * NS + j];
+          tr += L[i][i];
+        }
+        const double reg = 1e-13 * tr / NS;
+        double dinv[NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          double d = L[j][j] + reg;
+#pragma unroll
+          for (int c = 0; c < j; ++c) d -= L[j][c] * L[j][c];
+          if (!(d > 1e-300)) d = fmax(1e-8 * tr, 1e-300);   // repaired pivot (flags as numerical trouble downstream)
+          const double rs = rsqrt(d);
+          dinv[j] = rs;
+          L[j][j] = d * rs;
+#pragma unroll
+          for (int i = j + 1; i < NS; ++i) {
+            double v = L[i][j];
+#pragma unroll
+            for (int c = 0; c < j; ++c) v -= L[i][c] * L[j][c];
+            L[i][j] = v * rs;
+          }
+        }
+        // inverse of lower-triangular L (in place into Li)
+        double Li[NS][NS];
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+          Li[j][j] = dinv[j];
+#pragma unroll
+          for (int i = j + 1; i < NS; ++i) {
+            double v = 0.0;
+#pragma unroll
+            for (int c = j; c < i; ++c) v -= L[i][c] * Li[c][j];
+            Li[i][j] = v * dinv[i];
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+          for (int j = 0; j < NS; ++j)
+            if (lane == ((i * NS + j) & 31)) dk[i * NS + j] = (j <= i) ? Li[i][j] : 0.0;
+        __syncwarp();
+        // (d) Lo_k = E_k Li'   (E_k = H[k+1,k]); in place, so compute -> barrier -> store
+        {
+          double* ek = Ek + (size_t)k * SD;
+          double acc[2] = {0.0, 0.0};
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int idx = lane + 32 * t;
+            if (idx < NS * NS) {
+              const int i = idx / NS, j = idx % NS;
+#pragma unroll
+              for (int c = 0; c < NS; ++c) acc[t] += ek[i * NS + c] * dk[j * NS + c];
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const int idx = lane + 32 * t;
+            if (idx < NS * NS) ek[idx] = acc[t];
+          }
+        }
+        // fused forward substitution for 5 rhs: V_k = Li (R_k - Lo_{k-1} V_{k-1})
+        if (lane < 5 * NS) {
+          double r;
+          if (rc < 4) r = Rb[(size_t)k * SR + rc * NS + ri]; else r = dW[k * NSP + ri];
+          if (k > 1) {
+            const double* vp = (rc < 4) ? (Rb + (size_t)(k - 1) * SR + rc * NS) : (dW + (k - 1) * NSP);
+#pragma unroll
+            for (int c = 0; c < NS; ++c) r -= ekm[ri * NS + c] * vp[c];
+          }
+          red[32 + lane] = r;      // scratch (red[24..] unused during the sequential phase)
+        }
+        __syncwarp();
+        if (lane < 5 * NS) {
+          double v = 0.0;
+#pragma unroll
+          for (int c = 0; c < NS; ++c) v += dk[ri * NS + c] * red[32 + rc * NS + c];
+          if (rc < 4) Rb[(size_t)k * SR + rc * NS + ri] = v; else dW[k * NSP + ri] = v;
+        }
+        __syncwarp();
+      }
+      // Schur complement S = Gg - V'V  and  rg = bg - V' v   (V = L^-1 Bd, v = L^-1 b), lanes: 16 + 4
+      {
+        double acc = 0.0;
+        if (lane < 16) {
+          const int ca = lane >> 2, cb = lane & 3;
+          for (int k = 1; k < K - 1; ++k) {
+            const double* rb = Rb + (size_t)k * SR;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acc += rb[ca * NS + i] * rb[cb * NS + i];
+          }
+          gl[18 + lane] -= acc;
+        } else if (lane < 20) {
+          const int ca = lane - 16;
+          for (int k = 1; k < K - 1; ++k) {
+            const double* rb = Rb + (size_t)k * SR;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acc += rb[ca * NS + i] * dW[k * NSP + i];
+          }
+          gl[34 + ca] -= acc;
+        }
+      }
+      __syncwarp();
+      // backward substitution: Y_k = Li' (V_k - Lo_k' Y_{k+1})
+      for (int k = K - 2; k >= 1; --k) {
+        const double* dk = Dk + (size_t)k * SD;
+        if (lane < 5 * NS) {
+          double r;
+          if (rc < 4) r = Rb[(size_t)k * SR + rc * NS + ri]; else r = dW[k * NSP + ri];
+          if (k < K - 2) {
+            const double* lo = Ek + (size_t)k * SD;
+            const double* vn = (rc < 4) ? (Rb + (size_t)(k + 1) * SR + rc * NS) : (dW + (k + 1) * NSP);
+#pragma unroll
+            for (int c = 0; c < NS; ++c) r -= lo[c * NS + ri] * vn[c];
+          }
+          red[32 + lane] = r;
+        }
+        __syncwarp();
+        if (lane < 5 * NS) {
+          double v = 0.0;
+#pragma unroll
+          for (int c = 0; c < NS; ++c) v += dk[c * NS + ri] * red[32 + rc * NS + c];
+          if (rc < 4) Rb[(size_t)k * SR + rc * NS + ri] = v; else dW[k * NSP + ri] = v;
+        }
+        __syncwarp();
+      }
+      // 4x4 Schur solve (Cholesky) on lane 0; keeps the factor in gl[18..33] for the corrector
+      if (lane == 0) {
+        double S[4][4];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = gl[18 + i * 4 + j];
+        double tr = S[0][0] + S[1][1] + S[2][2] + S[3][3];
+        for (int j = 0; j < 4; ++j) {
+          double d = S[j][j] + 1e-14 * tr;
+          for (int c = 0; c < j; ++c) d -= S[j][c] * S[j][c];
+          if (!(d > 1e-300)) d = fmax(1e-10 * tr, 1e-300);
+          const double rs = rsqrt(d);
+          S[j][j] = d * rs;
+          for (int i = j + 1; i < 4; ++i) {
+            double v = S[i][j];
+            for (int c = 0; c < j; ++c) v -= S[i][c] * S[j][c];
+            S[i][j] = v * rs;
+          }
+        }
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) gl[18 + i * 4 + j] = S[i][j];
+        double y[4];
+        for (int i = 0; i < 4; ++i) { double v = gl[34 + i]; for (int c = 0; c < i; ++c) v -= S[i][c] * y[c]; y[i] = v / S[i][i]; }
+        for (int i = 3; i >= 0; --i) { double v = y[i]; for (int c = i + 1; c < 4; ++c) v -= S[c][i] * y[c]; y[i] = v / S[i][i]; }
+        for (int i = 0; i < 4; ++i) gl[4 + i] = y[i];
+      }
+    }
+    __syncthreads();
+    // dWa = v - Y dg_aff
+    {
+      const double g0 = gl[4], g1 = gl[5], g2 = gl[6], g3 = gl[7];
+      for (int k = tid; k < K; k += nthr) {
+        const bool fr = (k > 0 && k < K - 1);
+        const double* rb = Rb + (size_t)k * SR;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+          dWa[k * NSP + i] = fr ? dW[k * NSP + i] - (rb[i] * g0 + rb[NS + i] * g1 + rb[2 * NS + i] * g2 + rb[3 * NS + i] * g3) : 0.0;
+      }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------------------------ MODE 1/2/3/4
+    // A generic visitor over all rows of stage k.  For each row it provides (s, lambda, r_p, g.dz_aff, g.dz) and
+    // the address where the row state lives; F does the mode-specific work.
+    auto max_step = [](double v, double dv, double a) -> double { return (dv < 0.0) ? fmin(a, -v / dv) : a; };
+
+    for (int mode = 1; mode <= 4; ++mode) {
+      const double sigmu = gl[43];
+      const double al_p = gl[41], al_d = gl[42];
+      double pr[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pr[i] = 0.0;
+      pr[0] = 1.0; pr[1] = 1.0;
+      // pr: 0 alpha_p (min), 1 alpha_d (min), 2 sum ds*l, 3 sum s*dl, 4 sum ds*dl, 5..7 corrector bg pieces (t_nu, t_x, t_u), 8.. see below
+      double prg = 0.0;   // sigma-column piece of the corrector bg
+      const double ga0 = gl[4], ga1 = gl[5], ga2 = gl[6], ga3 = gl[7];     // affine global step
+      const double gd0 = gl[8], gd1 = gl[9], gd2 = gl[10], gd3 = gl[11];   // final global step
+      // per-row kernel: returns tau (mode 2) and updates statistics / state
+      auto row = [&](double* ps, double* pl, double gz_h, double gdza, double gdz, double& tau_out) {
+        const double s = *ps, l = *pl;
+        const double rp = gz_h + s, wgt = l / s;
+        const double dsa = -rp - gdza, dla = -l - wgt * dsa;
+        if (mode == 1) {
+          pr[0] = max_step(s, dsa, pr[0]); pr[1] = max_step(l, dla, pr[1]);
+          pr[2] += dsa * l; pr[3] += s * dla; pr[4] += dsa * dla;
+          return;
+        }
+        const double c2 = dsa * dla;
+        if (mode == 2) { tau_out = (sigmu - c2 + l * rp) / s; return; }
+        const double ds = -rp - gdz, dl = -l + (sigmu - c2) / s - wgt * ds;
+        if (mode == 3) { pr[0] = max_step(s, ds, pr[0]); pr[1] = max_step(l, dl, pr[1]); return; }
+        *ps = s + al_p * ds; *pl = l + al_d * dl;
+      };
+
+      for (int k = tid; k < K; k += nthr) {
+        const double* w = W + k * NSP;
+        const double* da = dWa + k * NSP;
+        const double* dz = dW + k * NSP;       // valid in modes 3, 4 (final direction)
+        const bool fr = (k > 0 && k < K - 1);
+        double bt[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) bt[i] = 0.0;
+        double* st = ST + (size_t)k * STG;
+        if (k < K - 1) {
+          const double* jac = JAC + (size_t)k * NJ;
+          double nu[NX], nua[NX], nud[NX] = {0, 0, 0};
+          nu_form<Dm, true>(jac, w, w + NSP, sig, nu);
+          nu_form<Dm, false>(jac, da, da + NSP, ga0, nua);
+          if (mode >= 3) nu_form<Dm, false>(jac, dz, dz + NSP, gd0, nud);
+          double et[NX] = {0, 0, 0}, stau = 0.0;
+#pragma unroll
+          for (int e = 0; e < NEX; ++e) {
+            const size_t o = (size_t)(Dm::R_NU + e) * K + k;
+            double f = -tnu, fa = -ga1, fd = -gd1;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { f += sgn(e, i) * nu[i]; fa += sgn(e, i) * nua[i]; fd += sgn(e, i) * nud[i]; }
+            double tau = 0.0;
+            row(ws.sP + o, ws.lP + o, f, fa, fd, tau);
+            if (mode == 2) {
+              stau += tau;
+#pragma unroll
+              for (int i = 0; i < NX; ++i) et[i] += tau * sgn(e, i);
+            }
+          }
+          if (mode == 2) {
+            const double* S = jac + NX * NX + 2 * NX * NU;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { st[10 + i] = et[i]; prg -= et[i] * S[i]; }
+            pr[5] -= stau;
+          }
+        }
+        {
+          double dx[NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) dx[i] = w[i] - Wr[k * NSP + i];
+          double stx = 0.0;
+#pragma unroll
+          for (int e = 0; e < NEX; ++e) {
+            const size_t o = (size_t)(Dm::R_X + e) * K + k;
+            double f = -tx, fa = -ga2, fd = -gd2;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { f += sgn(e, i) * dx[i]; fa += sgn(e, i) * da[i]; fd += sgn(e, i) * dz[i]; }
+            double tau = 0.0;
+            row(ws.sP + o, ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
+            if (mode == 2) {
+              stx += tau;
+#pragma unroll
+              for (int i = 0; i < NX; ++i) bt[i] += tau * sgn(e, i);
+            }
+          }
+          pr[6] -= stx;
+          double stu = 0.0;
+#pragma unroll
+          for (int e = 0; e < NEU; ++e) {
+            const size_t o = (size_t)(Dm::R_U + e) * K + k;
+            double f = -tu, fa = -ga3, fd = -gd3;
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+              f += sgn(e, j) * (w[NX + j] - Wr[k * NSP + NX + j]); fa += sgn(e, j) * da[NX + j]; fd += sgn(e, j) * dz[NX + j];
+            }
+            double tau = 0.0;
+            row(ws.sP + o, ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
+            if (mode == 2) {
+              stu += tau;
+#pragma unroll
+              for (int j = 0; j < NU; ++j) bt[NX + j] += tau * sgn(e, j);
+            }
+          }
+          pr[7] -= stu;
+        }
+        if (fr) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            double tau = 0.0;
+            size_t o = (size_t)(Dm::R_P + i) * K + k;
+            row(ws.sP + o, ws.lP + o, w[i] - sc.pos_hi, da[i], (mode >= 3) ? dz[i] : 0.0, tau);
+            if (mode == 2) bt[i] += tau;
+            o = (size_t)(Dm::R_P + D + i) * K + k;
+            row(ws.sP + o, ws.lP + o, sc.pos_lo - w[i], -da[i], (mode >= 3) ? -dz[i] : 0.0, tau);
+            if (mode == 2) bt[i] -= tau;
+          }
+          if (!BALL) {
+            const double gz[4] = {w[NX] - sc.v_max, -w[NX], w[NX + 1] - sc.w_max, -w[NX + 1] - sc.w_max};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              const size_t o = (size_t)(Dm::R_V + r) * K + k;
+              const int c = NX + (r >> 1);
+              const double sg = (r & 1) ? -1.0 : 1.0;
+              double tau = 0.0;
+              row(ws.sP + o, ws.lP + o, gz[r], sg * da[c], (mode >= 3) ? sg * dz[c] : 0.0, tau);
+              if (mode == 2) bt[c] += sg * tau;
+            }
+          } else {
+            const size_t o = (size_t)Dm::R_V * K + k;
+            double n2 = 0.0, uda = 0.0, udz = 0.0;
+#pragma unroll
+            for (int j = 0; j < NU; ++j) { n2 += w[NX + j] * w[NX + j]; uda += w[NX + j] * da[NX + j]; udz += w[NX + j] * dz[NX + j]; }
+            double tau = 0.0;
+            row(ws.sP + o, ws.lP + o, 0.5 * (n2 - sc.v_max * sc.v_max), uda, (mode >= 3) ? udz : 0.0, tau);
+            if (mode == 2) {
+#pragma unroll
+              for (int j = 0; j < NU; ++j) bt[NX + j] += tau * w[NX + j];
+            }
+          }
+          for (int h = 0; h < NH; ++h) {
+            if (!hinge_on(h)) continue;
+            double av[D], ap = 0.0, ada = 0.0, adz = 0.0;
+#pragma unroll
+            for (int c = 0; c < D; ++c) { av[c] = hinge_a(h, c, k); ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
+            const size_t o = (size_t)h * K + k;
+            const double xi = ws.xi[o], s1 = ws.s1[o], s2 = ws.s2[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
+            const double viol = hinge_b(h, k) - ap;
+            const double r1 = viol - xi + s1, r2 = -xi + s2;
+            const double w1 = l1 / s1, w2 = l2 / s2;
+            // affine step of this hinge pair (sigmu = 0, c = 0)
+            const double t1a = w1 * r1, t2a = w2 * r2;
+            const double rxa = -hw + t1a + t2a;
+            const double dxia = (rxa - w1 * ada) / (w1 + w2);
+            const double ds1a = -r1 + ada + dxia, ds2a = -r2 + dxia;
+            const double dl1a = -l1 - w1 * ds1a, dl2a = -l2 - w2 * ds2a;
+            if (mode == 1) {
+              pr[0] = max_step(s1, ds1a, pr[0]); pr[0] = max_step(s2, ds2a, pr[0]);
+              pr[1] = max_step(l1, dl1a, pr[1]); pr[1] = max_step(l2, dl2a, pr[1]);
+              pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += ds1a * dl1a + ds2a * dl2a;
+              continue;
+            }
+            const double c1 = ds1a * dl1a, c2 = ds2a * dl2a;
+            const double t1 = (sigmu - c1 + l1 * r1) / s1, t2 = (sigmu - c2 + l2 * r2) / s2;
+            const double rhs_xi = -hw + t1 + t2;
+            if (mode == 2) {
+              const double th = t1 - w1 * rhs_xi / (w1 + w2);
+#pragma unroll
+              for (int c = 0; c < D; ++c) bt[c] -= av[c] * th;
+              continue;
+            }
+            const double dxi = (rhs_xi - w1 * adz) / (w1 + w2);
+            const double ds1 = -r1 + adz + dxi, ds2 = -r2 + dxi;
+            const double dl1 = -l1 + (sigmu - c1) / s1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) / s2 - w2 * ds2;
+            if (mode == 3) {
+              pr[0] = max_step(s1, ds1, pr[0]); pr[0] = max_step(s2, ds2, pr[0]);
+              pr[1] = max_step(l1, dl1, pr[1]); pr[1] = max_step(l2, dl2, pr[1]);
+              continue;
+            }
+            ws.xi[o] = xi + al_p * dxi; ws.s1[o] = s1 + al_p * ds1; ws.s2[o] = s2 + al_p * ds2;
+            ws.l1[o] = l1 + al_d * dl1; ws.l2[o] = l2 + al_d * dl2;
+          }
+        }
+        if (mode == 2) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            const double ql = qlin ? qlin[(size_t)c * K + k] * sc.cs : 0.0;
+            bt[c] += sc.qrho * w[c] + ql;
+          }
+          // stash own-stage rhs piece; interval pieces are added after the barrier (dW is free: the affine
+          // direction lives in dWa)
+#pragma unroll
+          for (int i = 0; i < NS; ++i) dW[k * NSP + i] = bt[i];
+        }
+      }
+      // ---- mode epilogues
+      if (mode == 1) {
+        const int ops[5] = {1, 1, 0, 0, 0};
+        block_reduce<5>(pr, ops, red);
+        if (tid == 0) {
+          // global rows
+          double ap = red[0], ad = red[1], s2l = red[2], sdl = red[3], dd = red[4];
+          const double gG[3][4] = {{1, 0, 1, 1}, {-1, 0, 1, 1}, {-1, 0, 0, 0}};
+          for (int r = 0; r < 3; ++r) {
+            const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r], wgt = l / s;
+            const double gdza = gG[r][0] * ga0 + gG[r][2] * ga2 + gG[r][3] * ga3;
+            const double dsa = -rp - gdza, dla = -l - wgt * dsa;
+            ap = max_step(s, dsa, ap); ad = max_step(l, dla, ad);
+            s2l += dsa * l; sdl += s * dla; dd += dsa * dla;
+            gl[53 + r] = dsa * dla;
+          }
+          if (coupled) { ap = ad = fmin(ap, ad); }
+          const double comp = gl[45];
+          const double comp_aff = comp + ap * s2l + ad * sdl + ap * ad * dd;
+          double sg = comp_aff / comp;
+          sg = fmin(fmax(sg, 0.0), 1.0);
+          gl[43] = sg * sg * sg * gl[44];
+        }
+        __syncthreads();
+      } else if (mode == 2) {
+        pr[4] = prg;
+        __syncthreads();
+        for (int k = tid; k < K; k += nthr) {
+          const bool fr = (k > 0 && k < K - 1);
+          if (!fr) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) dW[k * NSP + i] = 0.0;
+            continue;
+          }
+          double acc[NS], t[NS];
+#pragma unroll
+          for (int i = 0; i < NS; ++i) acc[i] = dW[k * NSP + i];
+          JpT<Dm>(JAC + (size_t)k * NJ, ST + (size_t)k * STG + 10, t);
+#pragma unroll
+          for (int i = 0; i < NS; ++i) acc[i] += t[i];
+          JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ST + (size_t)(k - 1) * STG + 10, t);
+#pragma unroll
+          for (int i = 0; i < NS; ++i) dW[k * NSP + i] = -(acc[i] + t[i]);
+        }
+        const int ops[8] = {1, 1, 0, 0, 0, 0, 0, 0};
+        block_reduce<8>(pr, ops, red);
+        if (tid == 0) {
+          double bg[4] = {red[4], red[5], red[6], red[7]};
+          const double gG[3][4] = {{1, 0, 1, 1}, {-1, 0, 1, 1}, {-1, 0, 0, 0}};
+          for (int r = 0; r < 3; ++r) {
+            const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r];
+            const double tau = (sigmu - gl[53 + r] + l * rp) / s;
+            for (int i = 0; i < 4; ++i) bg[i] += gG[r][i] * tau;
+          }
+          bg[0] += sc.c_sig; bg[1] += sc.c_tnu;
+          for (int c = 0; c < 4; ++c) gl[34 + c] = -bg[c];
+        }
+        __syncthreads();
+        // corrector solve on warp 0: rg = bg - Y'b ; v = T^-1 b ; dg = S^-1 rg ; dW = v - Y dg
+        if (tid < 32) {
+          const int lane = tid;
+          if (lane < 4) {
+            double acc = 0.0;
+            for (int k = 1; k < K - 1; ++k) {
+              const double* rb = Rb + (size_t)k * SR;
+#pragma unroll
+              for (int i = 0; i < NS; ++i) acc += rb[lane * NS + i] * dW[k * NSP + i];
+            }
+            gl[34 + lane] -= acc;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            double S[4][4], y[4];
+            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = gl[18 + i * 4 + j];
+            for (int i = 0; i < 4; ++i) { double v = gl[34 + i]; for (int c = 0; c < i; ++c) v -= S[i][c] * y[c]; y[i] = v / S[i][i]; }
+            for (int i = 3; i >= 0; --i) { double v = y[i]; for (int c = i + 1; c < 4; ++c) v -= S[c][i] * y[c]; y[i] = v / S[i][i]; }
+            for (int i = 0; i < 4; ++i) gl[8 + i] = y[i];
+          }
+          __syncwarp();
+          // forward / backward substitution, single rhs, lanes 0..NS-1
+          for (int k = 1; k < K - 1; ++k) {
+            const double* dk = Dk + (size_t)k * SD;
+            if (lane < NS) {
+              double r = dW[k * NSP + lane];
+              if (k > 1) {
+                const double* lo = Ek + (size_t)(k - 1) * SD;
+#pragma unroll
+                for (int c = 0; c < NS; ++c) r -= lo[lane * NS + c] * dW[(k - 1) * NSP + c];
+              }
+              red[32 + lane] = r;
+            }
+            __syncwarp();
+            if (lane < NS) {
+              double v = 0.0;
+#pragma unroll
+              for (int c = 0; c < NS; ++c) v += dk[lane * NS + c] * red[32 + c];
+              dW[k * NSP + lane] = v;
+            }
+            __syncwarp();
+          }
+          for (int k = K - 2; k >= 1; --k) {
+            const double* dk = Dk + (size_t)k * SD;
+            if (lane < NS) {
+              double r = dW[k * NSP + lane];
+              if (k < K - 2) {
+                const double* lo = Ek + (size_t)k * SD;
+#pragma unroll
+                for (int c = 0; c < NS; ++c) r -= lo[c * NS + lane] * dW[(k + 1) * NSP + c];
+              }
+              red[32 + lane] = r;
+            }
+            __syncwarp();
+            if (lane < NS) {
+              double v = 0.0;
+#pragma unroll
+              for (int c = 0; c < NS; ++c) v += dk[c * NS + lane] * red[32 + c];
+              dW[k * NSP + lane] = v;
+            }
+            __syncwarp();
+          }
+        }
+        __syncthreads();
+        {
+          const double g0 = gl[8], g1 = gl[9], g2 = gl[10], g3 = gl[11];
+          for (int k = tid; k < K; k += nthr) {
+            const bool fr = (k > 0 && k < K - 1);
+            const double* rb = Rb + (size_t)k * SR;
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+              dW[k * NSP + i] = fr ? dW[k * NSP + i] - (rb[i] * g0 + rb[NS + i] * g1 + rb[2 * NS + i] * g2 + rb[3 * NS + i] * g3) : 0.0;
+          }
+        }
+        __syncthreads();
+      } else if (mode == 3) {
+        const int ops[2] = {1, 1};
+        block_reduce<2>(pr, ops, red);
+        if (tid == 0) {
+          double ap = red[0], ad = red[1];
+          const double gG[3][4] = {{1, 0, 1, 1}, {-1, 0, 1, 1}, {-1, 0, 0, 0}};
+          for (int r = 0; r < 3; ++r) {
+            const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r], wgt = l / s;
+            const double gdz = gG[r][0] * gd0 + gG[r][2] * gd2 + gG[r][3] * gd3;
+            const double ds = -rp - gdz, dl = -l + (sigmu - gl[53 + r]) / s - wgt * ds;
+            ap = max_step(s, ds, ap); ad = max_step(l, dl, ad);
+            gl[56 + r] = ds; gl[59 + r] = dl;
+          }
+          if (coupled) { ap = ad = fmin(ap, ad); }
+          gl[41] = fmin(1.0, 0.99 * ap); gl[42] = fmin(1.0, 0.99 * ad);
+        }
+        __syncthreads();
+      } else if (mode == 4) {
+        __syncthreads();
+        const double ap = gl[41], ad = gl[42];
+        for (int k = tid; k < K; k += nthr)
+#pragma unroll
+          for (int i = 0; i < NS; ++i) W[k * NSP + i] += ap * dW[k * NSP + i];
+        if (tid == 0) {
+          for (int c = 0; c < 4; ++c) gl[c] += ap * gl[8 + c];
+          for (int r = 0; r < 3; ++r) { gl[12 + r] += ap * gl[56 + r]; gl[15 + r] += ad * gl[59 + r]; }
+        }
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- epilogue: outputs in the reference's layouts --------------------------------------------------------
+  {
+    const double sig = gl[0];
+    double* Xo = a.X + (size_t)agent * NX * K;
+    double* Uo = a.U + (size_t)agent * NU * K;
+    double* No = a.nu + (size_t)agent * NX * (K - 1);
+    double pr[4] = {0.0, 0.0, 0.0, 0.0};   // max_k |nu_k|_1, sum obstacle slack, sum collision slack, quad+lin
+    for (int k = tid; k < K; k += nthr) {
+      const double* w = W + k * NSP;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) Xo[(size_t)i * K + k] = w[i];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) Uo[(size_t)j * K + k] = w[NX + j];
+      if (k < K - 1) {
+        double nu[NX], s = 0.0;
+        nu_form<Dm, true>(JAC + (size_t)k * NJ, w, w + NSP, sig, nu);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { No[(size_t)i * (K - 1) + k] = nu[i]; s += fabs(nu[i]); }
+        pr[0] = fmax(pr[0], s);
+      }
+      for (int h = 0; h < NH; ++h) {
+        double ap = 0.0;
+        const bool on = hinge_on(h);
+        if (on) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) ap += hinge_a(h, c, k) * w[c];
+        }
+        const double v = on ? fmax(0.0, hinge_b(h, k) - ap) : 0.0;
+        if (h < Mobs) { a.s_prime[((size_t)agent * Mobs + h) * K + k] = v; pr[1] += v; }
+        else {
+          if (a.col_slack) a.col_slack[((size_t)agent * a.n_nbr + (h - Mobs)) * K + k] = v;
+          pr[2] += v;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double ql = qlin ? qlin[(size_t)c * K + k] : 0.0;
+        pr[3] += 0.5 * (a.quad_rho ? a.quad_rho[agent] : 0.0) * w[c] * w[c] + ql * w[c];
+      }
+    }
+    const int ops[4] = {2, 0, 0, 0};
+    block_reduce<4>(pr, ops, red);
+    if (tid == 0) {
+      a.sigma[agent] = sig;
+      a.objective[agent] = a.weight_nu * red[0] + a.weight_slack * red[1] + a.weight_col * red[2] + a.weight_sigma * sig + red[3];
+      a.status[agent] = status;
+      a.iters[agent] = it;
+    }
+  }
+}
+
+template <class M>
+size_t solver_smem_bytes(int K) {
+  using Dm = Dims<M>;
+  return ((size_t)K * Dm::PER_STAGE + Dm::SMALL) * sizeof(double);
+}
+template <class M>
+size_t solver_ws_doubles_per_agent(int K, int NH) {
+  using Dm = Dims<M>;
+  return (size_t)K * (2 * Dm::NPLAIN + 5 * (size_t)NH);
+}
+
+template <class M>
+int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
+  const size_t smem = solver_smem_bytes<M>(a.K);
+  if (smem > 227 * 1024) {
+    snprintf(g_last_error, sizeof(g_last_error), "K=%d needs %zu B of shared memory per agent (> 227 KB)", a.K, smem);
+    return SCVX_E_UNSUPPORTED;
+  }
+  cudaError_t e = cudaFuncSetAttribute(ipm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  int threads = ((a.K + 31) / 32) * 32;
+  if (threads < 64) threads = 64;
+  if (threads > SOLVER_MAX_THREADS) threads = SOLVER_MAX_THREADS;
+  ipm_kernel<M><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9);
+  SCVX_CHECK_LAUNCH("scvx_solve_batched");
+  return SCVX_OK;
+}
+
+}  // namespace scvx
+
 using namespace scvx;
-extern "C" unsigned long long scvx_solve_workspace_bytes(int, int, int, int, int) { return 0ull; }
-extern "C" int scvx_solve_batched(const scvx_solve_args*, void*) {
-  snprintf(g_last_error, sizeof(g_last_error), "scvx_solve_batched: not built yet");
-  return SCVX_E_UNSUPPORTED;
+
+extern "C" unsigned long long scvx_solve_workspace_bytes(int model_id, int n_agents, int K, int M, int n_nbr) {
+  if (n_agents < 0 || K < 3 || M < 0 || n_nbr < 0) return 0ull;
+  size_t per;
+  switch (model_id) {
+    case SCVX_MODEL_UNICYCLE: per = solver_ws_doubles_per_agent<Unicycle>(K, M + n_nbr); break;
+    case SCVX_MODEL_SINGLE_INTEGRATOR: per = solver_ws_doubles_per_agent<SingleIntegrator>(K, M + n_nbr); break;
+    default: return 0ull;
+  }
+  return (unsigned long long)per * sizeof(double) * (unsigned long long)n_agents;
+}
+
+extern "C" int scvx_solve_batched(const scvx_solve_args* a, void* stream) {
+  if (!a) return bad_arg("args");
+  if (a->n_agents < 0 || a->K < 3 || a->M < 0 || a->n_nbr < 0) return bad_arg("n_agents/K/M/n_nbr");
+  if (a->n_agents == 0) return SCVX_OK;
+  if (!a->norm1_induced) {
+    snprintf(g_last_error, sizeof(g_last_error), "entry-wise L1 mode is not implemented (the reference uses the induced norm)");
+    return SCVX_E_UNSUPPORTED;
+  }
+  if (!a->A_bar || !a->B_bar || !a->C_bar || !a->S_bar || !a->z_bar || !a->X_ref || !a->U_ref || !a->sigma_ref ||
+      !a->tr_radius || !a->x_init || !a->x_final || !a->pos_lo || !a->pos_hi || !a->v_max || !a->X || !a->U || !a->nu ||
+      !a->sigma || !a->objective || !a->status || !a->iters)
+    return bad_arg("null pointer");
+  if (a->M > 0 && (!a->obs_a || !a->obs_b || !a->s_prime)) return bad_arg("obstacle tables");
+  if (a->n_nbr > 0 && (!a->col_a || !a->col_b)) return bad_arg("collision tables");
+  const unsigned long long need = scvx_solve_workspace_bytes(a->model_id, a->n_agents, a->K, a->M, a->n_nbr);
+  if (need == 0ull) return bad_arg("model_id");
+  if (!a->workspace || a->workspace_bytes < need) {
+    snprintf(g_last_error, sizeof(g_last_error), "workspace too small: need %llu bytes", need);
+    return SCVX_E_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (a->model_id) {
+    case SCVX_MODEL_UNICYCLE:
+      if (!a->w_max) return bad_arg("w_max");
+      return launch_ipm<Unicycle>(*a, st);
+    case SCVX_MODEL_SINGLE_INTEGRATOR:
+      return launch_ipm<SingleIntegrator>(*a, st);
+    default:
+      return bad_arg("model_id");
+  }
 }
