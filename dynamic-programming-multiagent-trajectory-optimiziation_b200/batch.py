@@ -1,0 +1,253 @@
+"""Device-resident batched drivers: the performance path of the SCvx inner loop.
+
+`AgentBatch`    -- constraint tables + trajectories of n agents of one model kind, on one GPU.
+`BatchedSCvx`   -- SCVXSolver.solve (SCvx/optimization/scvx_solver.py:33-115) for all agents at once:
+                   per outer iteration ONE launch each of the FOH kernel, the obstacle-linearisation
+                   kernel, the IPM kernel and the bookkeeping kernel; no host round trip inside the loop.
+`BatchedADMM`   -- ADMMCoordinator.solve / SI_ADMMCoordinator.solve (admm_coordinator.py:39-118,
+                   si_admm_coordinator.py:42-127) as Jacobi rounds, agents sharded over the ranks of a
+                   torch.distributed process group with ONE all-gather of positions per round.
+"""
+import numpy as np
+import torch
+
+from . import _device
+from .global_parameters import (CONV_TOL, MAX_ITER, TRUST_RADIUS0, WEIGHT_NU, WEIGHT_SIGMA, WEIGHT_SLACK)
+
+F64 = torch.float64
+WEIGHT_COLLISION_SLACK = 1e5     # SCvx/optimization/admm_utils.py:5
+_FAR = 1.0e3                     # padding obstacle: centre far outside the workspace, clearance -_FAR (never active)
+
+
+class AgentBatch:
+    def __init__(self, models, K, device=None):
+        if not models:
+            raise ValueError("empty agent batch")
+        mid = models[0].device_model_id
+        if mid is None or any(m.device_model_id != mid for m in models):
+            raise NotImplementedError("all agents of a batch must share one compiled device model")
+        self.models, self.K, self.n = list(models), K, len(models)
+        self.model_id = mid
+        self.n_x, self.n_u, self.d = _device.MODEL_DIMS[mid]
+        self.device = torch.device("cuda") if device is None else torch.device(device)
+        tabs = [m.get_constraints() for m in models]
+        self.M = max(len(t.obs_clearance) for t in tabs)
+        n, M, d = self.n, self.M, self.d
+        obs_c = np.full((n, M, d), _FAR)
+        obs_clear = np.full((n, M), -_FAR)
+        for i, t in enumerate(tabs):
+            m_i = len(t.obs_clearance)
+            if m_i:
+                obs_c[i, :m_i] = t.obs_centres
+                obs_clear[i, :m_i] = t.obs_clearance
+        self.n_obs = [len(t.obs_clearance) for t in tabs]
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)   # noqa: E731
+        self.x_init = up(np.stack([t.x_init for t in tabs]))
+        self.x_final = up(np.stack([t.x_final for t in tabs]))
+        self.pos_lo = up(np.array([t.pos_lo for t in tabs]))
+        self.pos_hi = up(np.array([t.pos_hi for t in tabs]))
+        self.v_max = up(np.array([t.v_max for t in tabs]))
+        self.w_max = up(np.array([t.w_max for t in tabs]))
+        self.obs_c, self.obs_clear = up(obs_c), up(obs_clear)
+
+    def initial_trajectories(self):
+        """model.initialize_trajectory for every agent (straight line, U = 0), built on the device."""
+        K = self.K
+        a2 = torch.arange(K, dtype=F64, device=self.device) / (K - 1)
+        X = self.x_init[:, :, None] * (1.0 - a2) + self.x_final[:, :, None] * a2
+        # the reference computes alpha1 = (K-1-k)/(K-1) separately; identical up to 1 ulp
+        U = torch.zeros((self.n, self.n_u, K), dtype=F64, device=self.device)
+        return X.contiguous(), U
+
+
+class BatchedSCvx:
+    """All agents run the reference's outer loop in lock step on the device."""
+
+    def __init__(self, models, K, max_iter=MAX_ITER, tr_radius0=TRUST_RADIUS0, conv_tol=CONV_TOL,
+                 weight_nu=WEIGHT_NU, weight_slack=WEIGHT_SLACK, weight_sigma=WEIGHT_SIGMA, n_sub=0,
+                 ipm_max_iter=0, device=None, batch=None):
+        self.batch = batch if batch is not None else AgentBatch(models, K, device)
+        b = self.batch
+        self.K, self.max_iter, self.tr_radius0, self.conv_tol = K, max_iter, tr_radius0, conv_tol
+        self.weight_nu, self.weight_slack, self.weight_sigma = weight_nu, weight_slack, weight_sigma
+        self.n_sub, self.ipm_max_iter = n_sub, ipm_max_iter
+        n, dev = b.n, b.device
+        self.ws = _device.SubproblemWorkspace(b.model_id, n, K, b.M, 0, dev)
+        self.mats = tuple(torch.empty((n, r, K - 1), dtype=F64, device=dev)
+                          for r in (b.n_x * b.n_x, b.n_x * b.n_u, b.n_x * b.n_u, b.n_x, b.n_x))
+        self.obs_a = torch.empty((n, b.M, b.d, K), dtype=F64, device=dev)
+        self.obs_b = torch.empty((n, b.M, K), dtype=F64, device=dev)
+        self.launches = 0
+
+    def iterate(self, X, U, sigma, tr, active, metrics_row):
+        """One outer iteration, in place on (X, U, sigma, tr, active): 4 kernel launches."""
+        b = self.batch
+        _device.foh(b.model_id, X, U, sigma, self.n_sub, out=self.mats)
+        if b.M:
+            _device.linearize_obstacles(b.model_id, X, b.obs_c, b.obs_clear, out=(self.obs_a, self.obs_b))
+        _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
+                                 b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
+                                 self.weight_sigma, max_iter=self.ipm_max_iter)
+        _device.outer_update(b.model_id, b.M, self.conv_tol, self.ws.X, self.ws.U, self.ws.nu, self.ws.sigma,
+                             self.ws.s_prime, X, U, sigma, tr, active, metrics_row)
+        self.launches += 4 if b.M else 3
+
+    def solve(self, X0=None, U0=None, initial_sigma=1.0, early_exit=True, check_every=5):
+        """Returns dict(X, U, sigma, metrics (iters, n, 6), n_iter (n,), status_hist (iters, n), objective_hist).
+        early_exit=False runs exactly max_iter outer iterations (throughput runs)."""
+        b = self.batch
+        n, dev = b.n, b.device
+        if X0 is None:
+            X, U = b.initial_trajectories()
+        else:
+            X, U = _device._dev(X0).clone(), _device._dev(U0).clone()
+        sigma = torch.full((n,), float(initial_sigma), dtype=F64, device=dev) if np.isscalar(initial_sigma) \
+            else _device._dev(initial_sigma).clone()
+        tr = torch.full((n,), float(self.tr_radius0), dtype=F64, device=dev)
+        active = torch.ones(n, dtype=torch.int32, device=dev)
+        metrics = torch.zeros((self.max_iter, n, 6), dtype=F64, device=dev)
+        status = torch.zeros((self.max_iter, n), dtype=torch.int32, device=dev)
+        ipm_iters = torch.zeros((self.max_iter, n), dtype=torch.int32, device=dev)
+        objective = torch.zeros((self.max_iter, n), dtype=F64, device=dev)
+        was_active = torch.zeros((self.max_iter, n), dtype=torch.int32, device=dev)
+        done = 0
+        for it in range(self.max_iter):
+            was_active[it].copy_(active)
+            self.iterate(X, U, sigma, tr, active, metrics[it])
+            status[it].copy_(self.ws.status); ipm_iters[it].copy_(self.ws.iters); objective[it].copy_(self.ws.objective)
+            done = it + 1
+            if early_exit and (it + 1) % check_every == 0 and int(active.sum().item()) == 0:
+                break
+        return {"X": X, "U": U, "sigma": sigma, "tr_radius": tr, "active": active, "metrics": metrics[:done],
+                "status": status[:done], "ipm_iters": ipm_iters[:done], "objective": objective[:done],
+                "was_active": was_active[:done], "n_outer": done}
+
+
+def shard_bounds(N, world, rank):
+    """Contiguous block partition of N agents over `world` ranks: (per, i0, i1) with per = ceil(N/world)."""
+    per = (N + world - 1) // world
+    i0 = min(rank * per, N)
+    return per, i0, min(i0 + per, N)
+
+
+def allgather_shards(X_local, U_local, N, per, dist=None, group=None):
+    """The ONE collective of an ADMM round: every rank contributes its shard's (X, U) -- padded to `per`
+    agents so that all ranks send the same count -- and receives all N agents' trajectories in agent order.
+    Works on any backend (NCCL on the GPUs; gloo in the CPU tests)."""
+    if dist is None or dist.get_world_size(group) == 1:
+        return X_local, U_local
+    world = dist.get_world_size(group)
+    nl, n_x, K = X_local.shape
+    n_u = U_local.shape[1]
+    send = torch.zeros((per, n_x + n_u, K), dtype=X_local.dtype, device=X_local.device)
+    if nl:
+        send[:nl, :n_x] = X_local
+        send[:nl, n_x:] = U_local
+    recv = torch.empty((world * per, n_x + n_u, K), dtype=X_local.dtype, device=X_local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    return recv[:N, :n_x].contiguous(), recv[:N, n_x:].contiguous()
+
+
+class BatchedADMM:
+    """Jacobi-sweep ADMM over N agents, optionally sharded across a process group.
+
+    Per round, for the local shard: FOH about the current own trajectory, obstacle + all-pairs inter-agent
+    linearisation about the gathered positions of the previous round, the QP/SOCP sub-problem
+    (agent_solver.py:79-102 collapsed to sum_j Y_j / sum_j Lambda_j), then ONE all-gather of
+    the new trajectories and the redundant per-j consensus update (admm_coordinator.py:80-96).
+    `si_variant=True` reproduces si_admm_coordinator.py:80-86 (trust region / obstacle linearisation about
+    the INITIAL references every round).
+    """
+
+    def __init__(self, models, d_min, K, rho_admm=1.0, max_iter=10, si_variant=False, group=None, device=None,
+                 n_sub=0, ipm_max_iter=0, neighbor_radius=None):
+        import torch.distributed as dist
+        self.dist = dist if (group is not None or (dist.is_available() and dist.is_initialized())) else None
+        self.group = group
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.N = len(models)
+        self.K, self.d_min, self.rho, self.max_iter, self.si_variant = K, float(d_min), float(rho_admm), max_iter, si_variant
+        self.n_sub, self.ipm_max_iter = n_sub, ipm_max_iter
+        self.neighbor_radius = neighbor_radius
+        self.per, self.i0, self.i1 = shard_bounds(self.N, self.world, self.rank)
+        self.nl = self.i1 - self.i0
+        self.all = AgentBatch(models, K, device)                       # tables for shapes / initial Y
+        self.local = AgentBatch(models[self.i0:self.i1], K, device) if self.nl else None
+        b = self.all
+        dev = b.device
+        if self.nl:
+            lb = self.local
+            self.ws = _device.SubproblemWorkspace(lb.model_id, self.nl, K, lb.M, self.N, dev)
+            self.mats = tuple(torch.empty((self.nl, r, K - 1), dtype=F64, device=dev)
+                              for r in (b.n_x * b.n_x, b.n_x * b.n_u, b.n_x * b.n_u, b.n_x, b.n_x))
+            self.obs_a = torch.empty((self.nl, lb.M, b.d, K), dtype=F64, device=dev)
+            self.obs_b = torch.empty((self.nl, lb.M, K), dtype=F64, device=dev)
+            self.col_a = torch.empty((self.nl, self.N, b.d, K), dtype=F64, device=dev)
+            self.col_b = torch.empty((self.nl, self.N, K), dtype=F64, device=dev)
+        self.launches = 0
+
+    def _gather(self, X_local, U_local):
+        return allgather_shards(X_local, U_local, self.N, self.per, self.dist, self.group)
+
+    def solve(self, X_refs, U_refs, sigma_ref):
+        """X_refs (N, n_x, K), U_refs (N, n_u, K) device tensors (every rank holds all of them).
+        Returns dict(X, U (all agents, on every rank), primal_hist, dual_hist, objective (rounds, N_local))."""
+        b = self.all
+        dev, K, N, d = b.device, self.K, self.N, b.d
+        X_all = _device._dev(X_refs).clone()
+        U_all = _device._dev(U_refs).clone()
+        Y = X_all[:, :d, :].contiguous().clone()                  # per-j consensus state
+        Lam = torch.zeros_like(Y)
+        X0_loc = X_all[self.i0:self.i1].clone(); U0_loc = U_all[self.i0:self.i1].clone()
+        sig = torch.full((max(self.nl, 1),), float(sigma_ref), dtype=F64, device=dev)[:self.nl]
+        tr = torch.full((max(self.nl, 1),), float(TRUST_RADIUS0), dtype=F64, device=dev)[:self.nl]
+        primal_hist, dual_hist, objs = [], [], []
+        mask = None
+        for _ in range(self.max_iter):
+            if self.nl:
+                lb = self.local
+                X_loc = X_all[self.i0:self.i1].contiguous(); U_loc = U_all[self.i0:self.i1].contiguous()
+                Xr, Ur = (X0_loc, U0_loc) if self.si_variant else (X_loc, U_loc)
+                _device.foh(lb.model_id, X_loc, U_loc, sig, self.n_sub, out=self.mats)
+                if lb.M:
+                    _device.linearize_obstacles(lb.model_id, Xr, lb.obs_c, lb.obs_clear, out=(self.obs_a, self.obs_b))
+                # a_ij about (own reference, neighbour's current trajectory); b = d_min + a.Y_j
+                _device.linearize_collision(lb.model_id, Xr, X_all, self.d_min, i0=self.i0, out=(self.col_a, self.col_b))
+                col_b = self.d_min + (self.col_a * Y[None]).sum(dim=2)
+                mask = torch.ones((self.nl, N), dtype=torch.uint8, device=dev)
+                mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
+                if self.neighbor_radius is not None:
+                    # neighbour culling (documented deviation for large N): keep j only if the trajectories come
+                    # within neighbor_radius at some node
+                    dist2 = ((Xr[:, None, :d, :] - X_all[None, :, :d, :]) ** 2).sum(dim=2).min(dim=2).values
+                    mask &= (dist2 <= self.neighbor_radius ** 2).to(torch.uint8)
+                nact = mask.sum(dim=1).to(F64)
+                # sum over ACTIVE neighbours of Y_j and Lambda_j  (all-pairs: total minus own)
+                mY = torch.einsum("ij,jdk->idk", mask.to(F64), Y)
+                mL = torch.einsum("ij,jdk->idk", mask.to(F64), Lam)
+                quad = self.rho * nact
+                lin = mL - self.rho * mY
+                _device.solve_subproblem(self.ws, self.mats, Xr, Ur, sig, tr, lb.x_init, lb.x_final, lb.pos_lo,
+                                         lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU,
+                                         WEIGHT_SLACK, WEIGHT_SIGMA, col_a=self.col_a, col_b=col_b, col_mask=mask,
+                                         quad_rho=quad, lin_p=lin, weight_col=WEIGHT_COLLISION_SLACK,
+                                         max_iter=self.ipm_max_iter)
+                # constant terms of the augmented Lagrangian so that `objective` matches agent_solver.py:92-95
+                yy = torch.einsum("ij,jdk->i", mask.to(F64), Y * Y)
+                ly = torch.einsum("ij,jdk->i", mask.to(F64), Lam * Y)
+                const = 0.5 * self.rho * yy - ly
+                objs.append((self.ws.objective + const).clone())
+                self.launches += 4 if lb.M else 3
+                X_new, U_new = self.ws.X, self.ws.U
+            else:
+                X_new = torch.empty((0, b.n_x, K), dtype=F64, device=dev); U_new = torch.empty((0, b.n_u, K), dtype=F64, device=dev)
+            X_all, U_all = self._gather(X_new, U_new)
+            X_all, U_all = X_all.clone(), U_all.clone()
+            P = X_all[:, :d, :].contiguous()
+            pr, du = _device.consensus_update(P, Y, Lam, self.rho)
+            self.launches += 1
+            primal_hist.append(pr.mean()); dual_hist.append(du.mean())
+        return {"X": X_all, "U": U_all, "Y": Y, "Lambda": Lam,
+                "primal_hist": torch.stack(primal_hist).cpu().tolist(), "dual_hist": torch.stack(dual_hist).cpu().tolist(),
+                "objective": torch.stack(objs) if objs else None, "mask": mask}

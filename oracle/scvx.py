@@ -76,6 +76,15 @@ def scvx_solve(model, K, max_iter=MAX_ITER, tr_radius=TRUST_RADIUS0, conv_tol=CO
     return X, U, sigma, records
 
 
+def _solve_qp(p):
+    """HiGHS' QP solver does not finish on these problems; the QP variant is solved with the CPU twin of
+    the interior-point algorithm and CERTIFIED by the exact LP bracket (subproblem.qp_bracket)."""
+    from .ipm_struct import StructIPM
+    s = StructIPM(p).solve()
+    ev = spb.evaluate(p, s["X"], s["U"], s["sigma"])
+    return {"ok": s["status"] == 0, "status": s["status"], "X": s["X"], "U": s["U"], "sigma": s["sigma"], "obj": ev["obj"]}
+
+
 def admm_solve(models, d_min, K, X_refs, U_refs, sigma_ref, rho=1.0, max_iter=10, sweep="gauss_seidel",
                si_variant=False, norm1_mode="induced", foh_tol="reference", solver="choose"):
     """admm_coordinator.py:39-118 (si_variant=True: si_admm_coordinator.py:80-86 passes the INITIAL
@@ -106,7 +115,7 @@ def admm_solve(models, d_min, K, X_refs, U_refs, sigma_ref, rho=1.0, max_iter=10
                 nbrs.append({"a": a, "Y": Y[j], "Lam": Lam[j]})
             p = spb.Params(models[i], K, mats, Xr, Ur, sigma_ref, TRUST_RADIUS0, WEIGHT_NU, WEIGHT_SLACK,
                            WEIGHT_SIGMA, norm1_mode, neighbors=nbrs, rho=rho, d_min=d_min)
-            r = spb.solve(p, solver=solver)
+            r = _solve_qp(p)
             if not r["ok"]:
                 raise RuntimeError(f"agent {i}: sub-problem status {r['status']}")
             round_objs.append(r["obj"])

@@ -121,8 +121,12 @@ class _Builder:
         self.m += 1
 
 
-def solve(p: Params, solver="choose", max_cuts=60):
-    """Solve the sub-problem exactly.  Returns dict(X, U, nu, sigma, s_prime, S, obj, status, ok)."""
+def solve(p: Params, solver="choose", max_cuts=60, linearize_at=None):
+    """Solve the sub-problem exactly.  Returns dict(X, U, nu, sigma, s_prime, S, obj, status, ok).
+
+    linearize_at = P0 (d, K): replace the quadratic term rho/2 * NB * |P|^2 of the ADMM variant by its
+    first-order model about P0.  The resulting LP's optimal value is a LOWER bound on the QP optimum
+    (convexity), and f(z0) - LB is the Frank-Wolfe gap of z0 -- see `qp_bracket`."""
     m, K = p.model, p.K
     n_x, n_u, d = m.n_x, m.n_u, m.d
     M, NB = len(m.obstacles), len(p.neighbors)
@@ -240,7 +244,14 @@ def solve(p: Params, solver="choose", max_cuts=60):
                     c[X(i, k)] += nb["Lam"][i, k] - p.rho * nb["Y"][i, k]
                     qdiag[X(i, k)] += p.rho
             offset += -(nb["Lam"] * nb["Y"]).sum() + 0.5 * p.rho * (nb["Y"] ** 2).sum()
-        Q = sp.diags(qdiag)
+        if linearize_at is None:
+            Q = sp.diags(qdiag)
+        else:
+            P0 = np.asarray(linearize_at, float)
+            for k in range(K):
+                for i in range(d):
+                    c[X(i, k)] += p.rho * NB * P0[i, k]
+            offset -= 0.5 * p.rho * NB * (P0 ** 2).sum()
 
     rows, cols, vals = list(b.rows), list(b.cols), list(b.vals)
     rlo, rhi = list(b.rlo), list(b.rhi)
@@ -273,3 +284,13 @@ def solve(p: Params, solver="choose", max_cuts=60):
     out["s_prime"] = x[iSp:iSp + M * K].reshape((M, K)).copy()
     out["S"] = [x[iS + q * K: iS + (q + 1) * K].copy() for q in range(NB)]
     return out
+
+
+def qp_bracket(p: Params, X, U, sigma):
+    """Exact optimality certificate for a candidate solution of the QP variant (agent_solver.py:79-102)
+    using only the exact LP solver: returns (f(z0), LB) with LB <= f_opt <= f(z0), where LB is the optimum
+    of the LP obtained by linearising the quadratic term about z0 (Frank-Wolfe gap).  HiGHS' own QP
+    active-set solver does not finish on these problems (>10 min at K=12), so QP parity is pinned this way."""
+    f0 = evaluate(p, X, U, sigma)
+    lb = solve(p, linearize_at=X[0:p.model.d, :])
+    return f0["obj"], lb["obj"], f0["viol"], lb["ok"]
