@@ -51,6 +51,8 @@ SIGNATURES = {
     "scvx_solve_batched": (_c_int, [ctypes.POINTER(SolveArgs), _c_dp]),
     "scvx_consensus_update": (_c_int, [_c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),
     "scvx_outer_update": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 11 + [_c_dp]),
+    "scvx_probe_fp64": (_c_int, [_c_int, _c_int, _c_dp, ctypes.POINTER(_c_dbl), _c_dp]),
+    "scvx_l2_flush": (_c_int, [_c_dp, ctypes.c_ulonglong, _c_dp]),
 }
 
 _lib = None

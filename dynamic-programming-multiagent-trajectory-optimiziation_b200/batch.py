@@ -79,18 +79,51 @@ class BatchedSCvx:
         self.obs_b = torch.empty((n, b.M, K), dtype=F64, device=dev)
         self.launches = 0
 
-    def iterate(self, X, U, sigma, tr, active, metrics_row):
-        """One outer iteration, in place on (X, U, sigma, tr, active): 4 kernel launches."""
+    def iterate(self, X, U, sigma, tr, active, metrics_row, solver_events=None):
+        """One outer iteration, in place on (X, U, sigma, tr, active): 4 kernel launches.
+        solver_events = (start, end) CUDA events recorded around the sub-problem kernel on the launching stream."""
         b = self.batch
         _device.foh(b.model_id, X, U, sigma, self.n_sub, out=self.mats)
         if b.M:
             _device.linearize_obstacles(b.model_id, X, b.obs_c, b.obs_clear, out=(self.obs_a, self.obs_b))
+        if solver_events is not None:
+            solver_events[0].record(torch.cuda.current_stream())
         _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
                                  b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
                                  self.weight_sigma, max_iter=self.ipm_max_iter)
+        if solver_events is not None:
+            solver_events[1].record(torch.cuda.current_stream())
         _device.outer_update(b.model_id, b.M, self.conv_tol, self.ws.X, self.ws.U, self.ws.nu, self.ws.sigma,
                              self.ws.s_prime, X, U, sigma, tr, active, metrics_row)
         self.launches += 4 if b.M else 3
+
+    # -- host-buffer API: the call a user holding numpy arrays makes ---------------------------------------------
+    def make_host_buffers(self):
+        """Pinned host staging for `iterate_host`: the iterate (X, U, sigma, tr, active) and the per-step metrics."""
+        b = self.batch
+        n, K = b.n, self.K
+        pin = lambda *shape, dtype=F64: torch.empty(shape, dtype=dtype).pin_memory()   # noqa: E731
+        host = {"X": pin(n, b.n_x, K), "U": pin(n, b.n_u, K), "sigma": pin(n), "tr": pin(n),
+                "active": torch.ones(n, dtype=torch.int32).pin_memory(), "metrics": pin(n, 6)}
+        dev = b.device
+        self._dbuf = {"X": torch.empty((n, b.n_x, K), dtype=F64, device=dev), "U": torch.empty((n, b.n_u, K), dtype=F64, device=dev),
+                      "sigma": torch.empty(n, dtype=F64, device=dev), "tr": torch.empty(n, dtype=F64, device=dev),
+                      "active": torch.empty(n, dtype=torch.int32, device=dev), "metrics": torch.empty((n, 6), dtype=F64, device=dev)}
+        self.h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in ("X", "U", "sigma", "tr", "active"))
+        self.d2h_bytes = sum(host[k].numel() * host[k].element_size() for k in ("X", "U", "sigma", "tr", "active", "metrics"))
+        return host
+
+    def iterate_host(self, host):
+        """One outer iteration with HOST buffers: H2D of the iterate, the four kernels, D2H of the new iterate and
+        the metrics (nu_norm, slack_norm, dx, du, ds, sigma) -- everything a host-side SCvx loop reads per iteration."""
+        d = self._dbuf
+        for k in ("X", "U", "sigma", "tr", "active"):
+            d[k].copy_(host[k], non_blocking=True)
+        self.iterate(d["X"], d["U"], d["sigma"], d["tr"], d["active"], d["metrics"])
+        for k in ("X", "U", "sigma", "tr", "active", "metrics"):
+            host[k].copy_(d[k], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return host
 
     def solve(self, X0=None, U0=None, initial_sigma=1.0, early_exit=True, check_every=5):
         """Returns dict(X, U, sigma, metrics (iters, n, 6), n_iter (n,), status_hist (iters, n), objective_hist).

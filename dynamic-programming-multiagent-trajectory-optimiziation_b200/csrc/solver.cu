@@ -758,7 +758,16 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
       gl[44] = mu; gl[45] = comp;
       int flag = 0;
       if (!(mu == mu) || !(rp_inf == rp_inf) || !(rd_inf == rd_inf) || mu > 1e300) flag = 2;
-      else if (comp <= eps_gap * fmax(fabs(obj), 1e-3) && rp_inf <= eps_feas && rd_inf <= 1e-6) flag = 1;
+      else {
+        // dual residual is judged relative to the largest (scaled) cost coefficient; once the gap is far past its
+        // target the residual sits at its round-off floor and a looser bound applies
+        double cmax = fmax(sc.c_tnu, sc.c_sig);
+        if (Mobs > 0) cmax = fmax(cmax, sc.hw_obs);
+        if (a.n_nbr > 0) cmax = fmax(cmax, sc.hw_col);
+        const double gscale = fmax(fabs(obj), 1e-3);
+        const bool gap_ok = comp <= eps_gap * gscale, deep = comp <= 1e-4 * eps_gap * gscale;
+        if (gap_ok && rp_inf <= eps_feas && rd_inf <= (deep ? 1e-5 : 1e-7) * (1.0 + cmax)) flag = 1;
+      }
       gl[40] = (double)flag;
     }
     __syncthreads();

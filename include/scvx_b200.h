@@ -172,6 +172,14 @@ int scvx_outer_update(int model_id, int n_agents, int K, int M, double conv_tol,
                       const double* s_prime, double* X, double* U, double* sigma, double* tr_radius,
                       int* active, double* metrics, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py only; not on the product path).
+ * scvx_probe_fp64: `blocks` x 256 threads x `iters` x 8 independent DFMA; *flops_h (HOST pointer) receives the flop
+ * count of the launch; `out` needs blocks*256 doubles.  scvx_l2_flush: write sweep over a buffer (> L2) between timed steps.
+ */
+int scvx_probe_fp64(int blocks, int iters, double* out, double* flops_h, void* stream);
+int scvx_l2_flush(double* buf, unsigned long long n_doubles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -161,7 +161,10 @@ class StructIPM:
                 + 0.5 * self.qrho * (W[:, :d] ** 2).sum() + (self.qlin.T * W[:, :d]).sum()
             if self.verbose:
                 print(f"{it:3d} mu={mu:.2e} rp={rp_inf:.2e} rd={rd_inf:.2e} obj={obj / self.cs:.8e}")
-            if comp <= self.eps_gap * max(abs(obj), 1e-3) and rp_inf <= self.eps_feas and rd_inf <= 1e-6:
+            cmax = max(self.c_tnu, self.c_sig, self.hw.max() if self.nh else 0.0)
+            gap_ok = comp <= self.eps_gap * max(abs(obj), 1e-3)
+            deep = comp <= 1e-4 * self.eps_gap * max(abs(obj), 1e-3)      # far past the gap target: rd is at its roundoff floor
+            if gap_ok and rp_inf <= self.eps_feas and rd_inf <= (1e-5 if deep else 1e-7) * (1.0 + cmax):
                 status = 0
                 break
             if not np.isfinite(mu):
