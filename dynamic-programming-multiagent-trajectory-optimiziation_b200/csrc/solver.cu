@@ -16,10 +16,13 @@
 //   from the Newton system, so the KKT matrix is block tridiagonal (n_s x n_s blocks, n_s = n_x + n_u) with a
 //   4-column border (sigma, t_nu, t_x, t_u) whatever the number of obstacles / neighbours.
 //
-// Per IPM iteration: row passes are data-parallel over stages (thread k owns stage k and interval k);
-// the block-Cholesky factorisation and the two substitution sweeps run on warp 0 with the whole factor
-// resident in shared memory; reductions use warp shuffles.  Row state (s, lambda) lives in a global workspace
-// laid out [row][k] so that every access is coalesced over k.
+// Per IPM iteration: row passes are data-parallel over stages (thread k owns stage k and interval k); the
+// block-tridiagonal system is factorised and solved by BLOCK CYCLIC REDUCTION (odd-even elimination, strides
+// 1, 2, 4, ...: log2(K) levels, every level data-parallel over (node, column) work items on all threads) with the
+// whole factor resident in shared memory; reductions use warp shuffles.  Row state (s, lambda) lives in a global
+// workspace laid out [row][k] so that every access is coalesced over k.
+// (The first version walked the stages sequentially on warp 0: profiles/r01a shows it latency-bound with 3 of 4
+// warps parked at a barrier; cyclic reduction removes the O(K) dependent chain.)
 #include "common.cuh"
 
 namespace scvx {
@@ -78,8 +81,10 @@ struct Dims {
   static constexpr int NSP = NS | 1;                      // padded stage stride (odd)
   static constexpr int SD = (NS * NS) | 1;                // padded block stride (odd)
   static constexpr int SR = (NS * 4) | 1;                 // padded border stride (odd)
-  static constexpr int STG = 17;                          // per-interval staging doubles (16 used)
-  static constexpr int PER_STAGE = 4 * NSP + NJ + 2 * SD + SR + STG;
+  static constexpr int STG = SD;                          // per-interval staging (16 used) ALIASES factor slot C
+  static constexpr int ST2 = 3;                           // corrector staging (e'tau of the interval)
+  static constexpr int PER_STAGE = 3 * NSP + NJ + 3 * SD + SR + ST2;
+  static constexpr int PER_STAGE_NOJAC = 3 * NSP + 3 * SD + SR + ST2;
   static constexpr int SMALL = 64 + 9 * 24;               // globals + reduction scratch
 };
 
@@ -176,10 +181,316 @@ struct Scal {
   double c_sig, c_tnu, cs, qrho, hw_obs, hw_col;
 };
 
+// ---- block cyclic reduction ------------------------------------------------------------------------
+// Free stages are the nodes p = 1..n (n = K-2) of an SPD block-tridiagonal system.  At stride s = 1, 2, 4, ... the
+// nodes p = s, 3s, 5s, ... are eliminated; per eliminated node j we keep
+//   slot A: Li_j  (inverse of the Cholesky factor of the pivot block; D_j^-1 v is applied as Li'(Li v): applying the
+//                  inverse FACTOR twice keeps the accuracy of triangular solves -- an explicit D^-1 does not, it costs
+//                  up to 2x the IPM iterations on ill-conditioned late iterates, see oracle/ipm_struct.py)
+//   slot B: P_j = D_j^-1 H[j, j-s]      slot C: Q_j = D_j^-1 H[j, j+s]
+// Work items are (node, column) pairs spread over all threads of the block.
+
+// Cholesky + triangular inverse of an NS x NS SPD block given by its lower triangle (registers, fully unrolled).
+// A pivot that has lost all significance is frozen (reciprocal 0): that row/column drops out of the step.
+template <int NS>
+__device__ __forceinline__ void chol_inverse(const double (*Din)[NS], double (*Li)[NS]) {
+  double L[NS][NS], dinv[NS];
+  double tr = 0.0;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) tr += Din[i][i];
+  const double reg = 1e-13 * tr / NS;
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    const double d0 = Din[j][j] + reg;
+    double d = d0;
+#pragma unroll
+    for (int c = 0; c < j; ++c) d -= L[j][c] * L[j][c];
+    const bool okp = d > 1e-12 * d0;
+    const double rs = okp ? rsqrt(d) : 0.0;
+    dinv[j] = rs;
+    L[j][j] = okp ? d * rs : 0.0;
+#pragma unroll
+    for (int i = j + 1; i < NS; ++i) {
+      double v = Din[i][j];
+#pragma unroll
+      for (int c = 0; c < j; ++c) v -= L[i][c] * L[j][c];
+      L[i][j] = v * rs;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    Li[j][j] = dinv[j];
+#pragma unroll
+    for (int i = j + 1; i < NS; ++i) {
+      double v = 0.0;
+#pragma unroll
+      for (int c = j; c < i; ++c) v -= L[i][c] * Li[c][j];
+      Li[i][j] = v * dinv[i];
+    }
+  }
+}
+// y = Li' (Li x)  with Li lower triangular
+template <int NS>
+__device__ __forceinline__ void apply_dinv(const double (*Li)[NS], const double* x, double* y) {
+  double t[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j <= i; ++j) acc += Li[i][j] * x[j];
+    t[i] = acc;
+  }
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    double acc = 0.0;
+#pragma unroll
+    for (int j = i; j < NS; ++j) acc += Li[j][i] * t[j];
+    y[i] = acc;
+  }
+}
+
+template <class Dm>
+__device__ __forceinline__ void cr_factor(double* A, double* B, double* C, int n, int tid, int nthr) {
+  constexpr int NS = Dm::NS, SD = Dm::SD;
+  for (int s = 1; s <= n; s <<= 1) {
+    const int cnt = (n / s + 1) >> 1;            // odd nodes j = s (2m+1) <= n
+    const int npr = nthr / NS;                   // nodes per round: the NS columns of a node always share a round
+    // ---- phase 1: pivot inverse, P, Q, push-left update of D_{j-s}
+    for (int base = 0; base < cnt; base += npr) {
+      const int m = base + tid / NS;
+      const bool on = (tid < npr * NS) && (m < cnt);
+      int j = 0, c = 0, a = 0, b = 0;
+      double Dl[NS][NS], Lj[NS][NS];
+      if (on) {
+        c = tid - (tid / NS) * NS;
+        j = s * (2 * m + 1); a = j - s; b = j + s;
+        const double* dj = A + (size_t)j * SD;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+          for (int q = 0; q <= i; ++q) Dl[i][q] = dj[i * NS + q];
+        const double* lj = B + (size_t)j * SD;
+#pragma unroll
+        for (int i = 0; i < NS; ++i)
+#pragma unroll
+          for (int q = 0; q < NS; ++q) Lj[i][q] = (a >= 1) ? lj[i * NS + q] : 0.0;
+      }
+      __syncthreads();
+      if (on) {
+        double Li[NS][NS];
+        chol_inverse<NS>(Dl, Li);
+        if (c == 0) {
+          double* dj = A + (size_t)j * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i)
+#pragma unroll
+            for (int q = 0; q < NS; ++q) dj[i * NS + q] = (q <= i) ? Li[i][q] : 0.0;
+        }
+        double x[NS], pc[NS], qc[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) x[i] = Lj[i][c];
+        apply_dinv<NS>(Li, x, pc);
+        double* pj = B + (size_t)j * SD;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) pj[i * NS + c] = pc[i];
+        if (a >= 1) {
+          double* da = A + (size_t)a * SD;
+#pragma unroll
+          for (int r = 0; r < NS; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acc += Lj[i][r] * pc[i];
+            da[r * NS + c] -= acc;
+          }
+        }
+        if (b <= n) {
+          const double* lb = B + (size_t)b * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) x[i] = lb[c * NS + i];      // column c of H[j, b] = row c of H[b, j]
+          apply_dinv<NS>(Li, x, qc);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) qc[i] = 0.0;
+        }
+        double* qj = C + (size_t)j * SD;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) qj[i * NS + c] = qc[i];
+      }
+      __syncthreads();
+    }
+    // ---- phase 2: push-right update of D_{j+s} and the new left coupling of node j+s
+    for (int base = 0; base < cnt; base += npr) {
+      const int m = base + tid / NS;
+      int j = 0, c = 0, b = 0;
+      bool on = (tid < npr * NS) && (m < cnt);
+      double Lb[NS][NS];
+      if (on) {
+        c = tid - (tid / NS) * NS;
+        j = s * (2 * m + 1); b = j + s;
+        on = (b <= n);
+        if (on) {
+          const double* lb = B + (size_t)b * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i)
+#pragma unroll
+            for (int q = 0; q < NS; ++q) Lb[i][q] = lb[i * NS + q];
+        }
+      }
+      __syncthreads();
+      if (on) {
+        const double* pj = B + (size_t)j * SD;
+        const double* qj = C + (size_t)j * SD;
+        double* db = A + (size_t)b * SD;
+        double* lb = B + (size_t)b * SD;
+        double pc[NS], qc[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { pc[i] = pj[i * NS + c]; qc[i] = qj[i * NS + c]; }
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+          double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) { a1 += Lb[r][i] * qc[i]; a2 += Lb[r][i] * pc[i]; }
+          db[r * NS + c] -= a1;
+          lb[r * NS + c] = -a2;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// rhs columns: c < 4 -> border column c (Rb), c == 4 -> the Newton rhs (dW).  NC = 5: all of them, NC = 1: only dW.
+template <class Dm, int NC>
+__device__ __forceinline__ double* rhs_col(double* Rb, double* dW, int k, int c) {
+  return (NC == 1 || c == 4) ? (dW + (size_t)k * Dm::NSP) : (Rb + (size_t)k * Dm::SR + c * Dm::NS);
+}
+
+template <class Dm, int NC>
+__device__ __forceinline__ void cr_forward(const double* B, const double* C, double* Rb, double* dW, int n, int tid, int nthr) {
+  constexpr int NS = Dm::NS, SD = Dm::SD;
+  for (int s = 1; 2 * s <= n; s <<= 1) {
+    const int items = (n / (2 * s)) * NC;          // even nodes a = 2 s (m+1)
+    for (int it = tid; it < items; it += nthr) {
+      const int m = it / NC, c = (NC == 1) ? 4 : it - m * NC;
+      const int a = 2 * s * (m + 1), jl = a - s, jr = a + s;
+      double* va = rhs_col<Dm, NC>(Rb, dW, a, c);
+      const double* vl = rhs_col<Dm, NC>(Rb, dW, jl, c);
+      const double* ql = C + (size_t)jl * SD;
+      double v[NS];
+#pragma unroll
+      for (int r = 0; r < NS; ++r) {
+        double acc = va[r];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) acc -= ql[i * NS + r] * vl[i];
+        v[r] = acc;
+      }
+      if (jr <= n) {
+        const double* vr = rhs_col<Dm, NC>(Rb, dW, jr, c);
+        const double* pr = B + (size_t)jr * SD;
+#pragma unroll
+        for (int r = 0; r < NS; ++r) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) acc += pr[i * NS + r] * vr[i];
+          v[r] -= acc;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NS; ++r) va[r] = v[r];
+    }
+    __syncthreads();
+  }
+  if (n < 2) __syncthreads();
+}
+
+template <class Dm, int NC>
+__device__ __forceinline__ void cr_backward(const double* A, const double* B, const double* C, double* Rb, double* dW, int n,
+                                            int tid, int nthr) {
+  constexpr int NS = Dm::NS, SD = Dm::SD;
+  int s = 1;
+  while (2 * s <= n) s <<= 1;
+  for (; s >= 1; s >>= 1) {
+    const int items = ((n / s + 1) >> 1) * NC;     // odd nodes j = s (2m+1)
+    for (int it = tid; it < items; it += nthr) {
+      const int m = it / NC, c = (NC == 1) ? 4 : it - m * NC;
+      const int j = s * (2 * m + 1), jl = j - s, jr = j + s;
+      double* vj = rhs_col<Dm, NC>(Rb, dW, j, c);
+      const double* li = A + (size_t)j * SD;
+      double t[NS], x[NS];
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q <= i; ++q) acc += li[i * NS + q] * vj[q];
+        t[i] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int q = i; q < NS; ++q) acc += li[q * NS + i] * t[q];
+        x[i] = acc;
+      }
+      if (jl >= 1) {
+        const double* vl = rhs_col<Dm, NC>(Rb, dW, jl, c);
+        const double* pj = B + (size_t)j * SD;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int q = 0; q < NS; ++q) acc += pj[i * NS + q] * vl[q];
+          x[i] -= acc;
+        }
+      }
+      if (jr <= n) {
+        const double* vr = rhs_col<Dm, NC>(Rb, dW, jr, c);
+        const double* qj = C + (size_t)j * SD;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          double acc = 0.0;
+#pragma unroll
+          for (int q = 0; q < NS; ++q) acc += qj[i * NS + q] * vr[q];
+          x[i] -= acc;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NS; ++i) vj[i] = x[i];
+    }
+    __syncthreads();
+  }
+}
+
+// 4x4 Schur complement: Cholesky in place (kept for the corrector), then solve.
+__device__ __forceinline__ void schur_solve(const double* Sf, const double* rhs, double* out) {
+  double y[4];
+  for (int i = 0; i < 4; ++i) { double v = rhs[i]; for (int c = 0; c < i; ++c) v -= Sf[i * 4 + c] * y[c]; y[i] = v / Sf[i * 4 + i]; }
+  for (int i = 3; i >= 0; --i) { double v = y[i]; for (int c = i + 1; c < 4; ++c) v -= Sf[c * 4 + i] * y[c]; y[i] = v / Sf[i * 4 + i]; }
+  for (int i = 0; i < 4; ++i) out[i] = y[i];
+}
+__device__ __forceinline__ void schur_factor_solve(double* Sm, const double* rhs, double* out) {
+  double S[4][4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = Sm[i * 4 + j];
+  const double tr = S[0][0] + S[1][1] + S[2][2] + S[3][3];
+  for (int j = 0; j < 4; ++j) {
+    double d = S[j][j] + 1e-14 * tr;
+    for (int c = 0; c < j; ++c) d -= S[j][c] * S[j][c];
+    if (!(d > 1e-300)) d = fmax(1e-10 * tr, 1e-300);
+    const double rs = rsqrt(d);
+    S[j][j] = d * rs;
+    for (int i = j + 1; i < 4; ++i) {
+      double v = S[i][j];
+      for (int c = 0; c < j; ++c) v -= S[i][c] * S[j][c];
+      S[i][j] = v * rs;
+    }
+  }
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Sm[i * 4 + j] = S[i][j];
+  schur_solve(Sm, rhs, out);
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 template <class M>
 __global__ void __launch_bounds__(SOLVER_MAX_THREADS, 1)
-ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
+ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int jac_in_smem, size_t jac_ws_offset) {
   using Dm = Dims<M>;
   constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
   constexpr int NSP = Dm::NSP, SD = Dm::SD, SR = Dm::SR, NJ = Dm::NJ, STG = Dm::STG, NPLAIN = Dm::NPLAIN;
@@ -189,16 +500,18 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
 
   extern __shared__ __align__(16) double smem[];
   double* W = smem;                     // [K][NSP] current stage variables
-  double* Wr = W + (size_t)K * NSP;     // [K][NSP] trust-region centre
-  double* dWa = Wr + (size_t)K * NSP;   // [K][NSP] affine (predictor) direction
+  double* dWa = W + (size_t)K * NSP;    // [K][NSP] affine (predictor) direction
   double* dW = dWa + (size_t)K * NSP;   // [K][NSP] rhs / solution of the current solve
-  double* JAC = dW + (size_t)K * NSP;   // [K][NJ]
-  double* Dk = JAC + (size_t)K * NJ;    // [K][SD]   diagonal blocks -> Li (inverse Cholesky factor)
-  double* Ek = Dk + (size_t)K * SD;     // [K][SD]   sub-diagonal blocks H[k+1,k] -> Lo
-  double* Rb = Ek + (size_t)K * SD;     // [K][SR]   border columns Bd -> Y = T^-1 Bd     layout [c*NS + i]
-  double* ST = Rb + (size_t)K * SR;     // [K][STG]  per-interval staging
-  double* gl = ST + (size_t)K * STG;    // [64] globals
+  double* Dk = dW + (size_t)K * NSP;    // [K][SD]  slot A: diagonal blocks -> Li (inverse Cholesky factor of the pivot block)
+  double* Ek = Dk + (size_t)K * SD;     // [K][SD]  slot B: coupling to the current left neighbour H[k, k-s] -> P_k
+  double* Ck = Ek + (size_t)K * SD;     // [K][SD]  slot C: Q_k (aliased by the assembly staging ST before the factorisation)
+  double* Rb = Ck + (size_t)K * SD;     // [K][SR]  border columns Bd -> Y = T^-1 Bd     layout [c*NS + i]
+  double* ST2 = Rb + (size_t)K * SR;    // [K][3]   corrector staging
+  double* gl = ST2 + (size_t)K * Dm::ST2;   // [64] globals
   double* red = gl + 64;                // [9][24] reduction scratch
+  double* ST = Ck;                      // per-interval staging of the assembly pass (16 of SD doubles)
+  // interval Jacobians [K][NJ]: shared memory when it fits, else a slice of the global workspace
+  double* JAC = jac_in_smem ? (red + 9 * 24) : ((double*)a.workspace + jac_ws_offset + (size_t)agent * K * NJ);
   // globals: gl[0..3] = sigma, t_nu, t_x, t_u ; gl[4..7] = dg_aff ; gl[8..11] = dg ; gl[12..14] sG ; gl[15..17] lG ;
   // gl[18..33] = Gg/S 4x4 ; gl[34..37] = bg ; gl[40] flag ; gl[41] alpha_p ; gl[42] alpha_d ; gl[43] sigmu ; gl[44] mu
   // gl[45] comp ; gl[46..49] Y'b scratch
@@ -237,15 +550,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
   auto hinge_w = [&](int h) -> double { return (h < Mobs) ? sc.hw_obs : sc.hw_col; };
 
   // ---- load problem data into shared memory ---------------------------------------------------------
+  const double* Xr = a.X_ref + (size_t)agent * NX * K;
+  const double* Ur = a.U_ref + (size_t)agent * NU * K;
+  // trust-region centre, read from global memory (coalesced over k; L1/L2 resident)
+  auto WR = [&](int k, int i) -> double { return (i < NX) ? Xr[(size_t)i * K + k] : Ur[(size_t)(i - NX) * K + k]; };
   {
-    const double* Xr = a.X_ref + (size_t)agent * NX * K;
-    const double* Ur = a.U_ref + (size_t)agent * NU * K;
-    for (int k = tid; k < K; k += nthr) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) Wr[k * NSP + i] = Xr[(size_t)i * K + k];
-#pragma unroll
-      for (int j = 0; j < NU; ++j) Wr[k * NSP + NX + j] = Ur[(size_t)j * K + k];
-    }
     const int Km1 = K - 1;
     const double* Ab = a.A_bar + (size_t)agent * NX * NX * Km1;
     const double* Bb = a.B_bar + (size_t)agent * NX * NU * Km1;
@@ -279,7 +588,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
         for (int j = 0; j < NU; ++j) w[NX + j] = 0.0;
       } else {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) w[i] = Wr[k * NSP + i];
+        for (int i = 0; i < NS; ++i) w[i] = WR(k, i);
 #pragma unroll
         for (int i = 0; i < D; ++i) w[i] = fmin(fmax(w[i], sc.pos_lo + dlt), sc.pos_hi - dlt);
         if (!BALL) {
@@ -315,9 +624,9 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
       }
       double sx = 0.0, su = 0.0;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) sx += fabs(w[i] - Wr[k * NSP + i]);
+      for (int i = 0; i < NX; ++i) sx += fabs(w[i] - WR(k, i));
 #pragma unroll
-      for (int j = 0; j < NU; ++j) su += fabs(w[NX + j] - Wr[k * NSP + NX + j]);
+      for (int j = 0; j < NU; ++j) su += fabs(w[NX + j] - WR(k, NX + j));
       v[1] = fmax(v[1], sx); v[2] = fmax(v[2], su);
     }
     const int ops[3] = {2, 2, 2};
@@ -350,7 +659,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
     for (int e = 0; e < NEX; ++e) {
       double f = -tx;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) f += sgn(e, i) * (w[i] - Wr[k * NSP + i]);
+      for (int i = 0; i < NX; ++i) f += sgn(e, i) * (w[i] - WR(k, i));
       const double s = fmax(-f, 1e-8);
       ws.sP[(size_t)(Dm::R_X + e) * K + k] = s; ws.lP[(size_t)(Dm::R_X + e) * K + k] = mu0 / s;
     }
@@ -358,7 +667,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
     for (int e = 0; e < NEU; ++e) {
       double f = -tu;
 #pragma unroll
-      for (int j = 0; j < NU; ++j) f += sgn(e, j) * (w[NX + j] - Wr[k * NSP + NX + j]);
+      for (int j = 0; j < NU; ++j) f += sgn(e, j) * (w[NX + j] - WR(k, NX + j));
       const double s = fmax(-f, 1e-8);
       ws.sP[(size_t)(Dm::R_U + e) * K + k] = s; ws.lP[(size_t)(Dm::R_U + e) * K + k] = mu0 / s;
     }
@@ -481,7 +790,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
       {
         double dx[NX], mvx[NX] = {0, 0, 0}, swx = 0.0, stx = 0.0, slx = 0.0;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) dx[i] = w[i] - Wr[k * NSP + i];
+        for (int i = 0; i < NX; ++i) dx[i] = w[i] - WR(k, i);
 #pragma unroll
         for (int e = 0; e < NEX; ++e) {
           const size_t o = (size_t)(Dm::R_X + e) * K + k;
@@ -507,7 +816,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
       {
         double du[NU], mvu[NU], swu = 0.0, stu = 0.0, slu = 0.0;
 #pragma unroll
-        for (int j = 0; j < NU; ++j) { du[j] = w[NX + j] - Wr[k * NSP + NX + j]; mvu[j] = 0.0; }
+        for (int j = 0; j < NU; ++j) { du[j] = w[NX + j] - WR(k, NX + j); mvu[j] = 0.0; }
 #pragma unroll
         for (int e = 0; e < NEU; ++e) {
           const size_t o = (size_t)(Dm::R_U + e) * K + k;
@@ -626,7 +935,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
     for (int k = tid; k < K; k += nthr) {
       const bool fr = (k > 0 && k < K - 1);
       double* dk = Dk + (size_t)k * SD;
-      double* ek = Ek + (size_t)k * SD;
+      double* ek = Ek + (size_t)(k + 1 < K ? k + 1 : k) * SD;    // slot B of stage k+1 holds H[k+1, k]
       double* rb = Rb + (size_t)k * SR;
       if (!fr) {
 #pragma unroll
@@ -777,184 +1086,55 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
       if (flag == 2) { status = SCVX_ST_NUMERICAL; break; }
     }
 
-    // ------------------------------------------------------------------- factor + predictor solve (warp 0)
-    // Block Cholesky of the tridiagonal part; diagonal blocks are replaced by Li = L^-1 (lower), sub-diagonal
-    // blocks by Lo_k = E_k Li_k'.  Forward substitution of the 4 border columns + the rhs is fused in.
-    if (tid < 32) {
-      const int lane = tid;
-      const int rc = lane / NS, ri = lane % NS;             // (rhs column 0..4, component) role for 5*NS lanes
-      double sacc[10];                                      // Schur accumulators  V'V (10 unique) -- lanes cooperate below
-      (void)sacc;
-      for (int k = 1; k < K - 1; ++k) {
-        double* dk = Dk + (size_t)k * SD;
-        double* ekm = Ek + (size_t)(k - 1) * SD;            // Lo_{k-1}
-        // (a) Dk -= Lo_{k-1} Lo_{k-1}'
-        for (int idx = lane; idx < NS * NS; idx += 32) {
-          const int i = idx / NS, j = idx % NS;
-          double acc = dk[idx];
+    // ------------------------------------------------------------------- factor + predictor solve (all threads)
+    cr_factor<Dm>(Dk, Ek, Ck, K - 2, tid, nthr);
+    cr_forward<Dm, 5>(Ek, Ck, Rb, dW, K - 2, tid, nthr);
+    // Schur complement of the border:  S = Gg - sum_j (Li_j V_j)'(Li_j V_j),  rg = bg - sum_j (Li_j V_j)'(Li_j v_j)
+    {
+      double sp[14];
 #pragma unroll
-          for (int c = 0; c < NS; ++c) acc -= ekm[i * NS + c] * ekm[j * NS + c];
-          dk[idx] = acc;
-        }
-        __syncwarp();
-        // (b,c) every lane: Cholesky + inverse of the NS x NS block in registers
-        double L[NS][NS];
-        double tr = 0.0;
+      for (int i = 0; i < 14; ++i) sp[i] = 0.0;
+      for (int k = 1 + tid; k <= K - 2; k += nthr) {
+        const double* li = Dk + (size_t)k * SD;
+        double Z[5][NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
+        for (int c = 0; c < 5; ++c) {
+          const double* v = (c < 4) ? (Rb + (size_t)k * SR + c * NS) : (dW + k * NSP);
 #pragma unroll
-          for (int j = 0; j <= i; ++j) L[i][j] = dk[i * NS + j];
-          tr += L[i][i];
-        }
-        const double reg = 1e-13 * tr / NS;
-        double dinv[NS];
+          for (int i = 0; i < NS; ++i) {
+            double acc = 0.0;
 #pragma unroll
-        for (int j = 0; j < NS; ++j) {
-          double d = L[j][j] + reg;
-#pragma unroll
-          for (int c = 0; c < j; ++c) d -= L[j][c] * L[j][c];
-          if (!(d > 1e-300)) d = fmax(1e-8 * tr, 1e-300);   // repaired pivot (flags as numerical trouble downstream)
-          const double rs = rsqrt(d);
-          dinv[j] = rs;
-          L[j][j] = d * rs;
-#pragma unroll
-          for (int i = j + 1; i < NS; ++i) {
-            double v = L[i][j];
-#pragma unroll
-            for (int c = 0; c < j; ++c) v -= L[i][c] * L[j][c];
-            L[i][j] = v * rs;
+            for (int j = 0; j <= i; ++j) acc += li[i * NS + j] * v[j];
+            Z[c][i] = acc;
           }
         }
-        // inverse of lower-triangular L (in place into Li)
-        double Li[NS][NS];
+        int q = 0;
 #pragma unroll
-        for (int j = 0; j < NS; ++j) {
-          Li[j][j] = dinv[j];
+        for (int ca = 0; ca < 4; ++ca)
 #pragma unroll
-          for (int i = j + 1; i < NS; ++i) {
-            double v = 0.0;
+          for (int cb = ca; cb < 5; ++cb) {
+            double acc = 0.0;
 #pragma unroll
-            for (int c = j; c < i; ++c) v -= L[i][c] * Li[c][j];
-            Li[i][j] = v * dinv[i];
+            for (int i = 0; i < NS; ++i) acc += Z[ca][i] * Z[cb][i];
+            sp[q++] += acc;
           }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < NS; ++i)
-#pragma unroll
-          for (int j = 0; j < NS; ++j)
-            if (lane == ((i * NS + j) & 31)) dk[i * NS + j] = (j <= i) ? Li[i][j] : 0.0;
-        __syncwarp();
-        // (d) Lo_k = E_k Li'   (E_k = H[k+1,k]); in place, so compute -> barrier -> store
-        {
-          double* ek = Ek + (size_t)k * SD;
-          double acc[2] = {0.0, 0.0};
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int idx = lane + 32 * t;
-            if (idx < NS * NS) {
-              const int i = idx / NS, j = idx % NS;
-#pragma unroll
-              for (int c = 0; c < NS; ++c) acc[t] += ek[i * NS + c] * dk[j * NS + c];
-            }
-          }
-          __syncwarp();
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int idx = lane + 32 * t;
-            if (idx < NS * NS) ek[idx] = acc[t];
-          }
-        }
-        // fused forward substitution for 5 rhs: V_k = Li (R_k - Lo_{k-1} V_{k-1})
-        if (lane < 5 * NS) {
-          double r;
-          if (rc < 4) r = Rb[(size_t)k * SR + rc * NS + ri]; else r = dW[k * NSP + ri];
-          if (k > 1) {
-            const double* vp = (rc < 4) ? (Rb + (size_t)(k - 1) * SR + rc * NS) : (dW + (k - 1) * NSP);
-#pragma unroll
-            for (int c = 0; c < NS; ++c) r -= ekm[ri * NS + c] * vp[c];
-          }
-          red[32 + lane] = r;      // scratch (red[24..] unused during the sequential phase)
-        }
-        __syncwarp();
-        if (lane < 5 * NS) {
-          double v = 0.0;
-#pragma unroll
-          for (int c = 0; c < NS; ++c) v += dk[ri * NS + c] * red[32 + rc * NS + c];
-          if (rc < 4) Rb[(size_t)k * SR + rc * NS + ri] = v; else dW[k * NSP + ri] = v;
-        }
-        __syncwarp();
       }
-      // Schur complement S = Gg - V'V  and  rg = bg - V' v   (V = L^-1 Bd, v = L^-1 b), lanes: 16 + 4
-      {
-        double acc = 0.0;
-        if (lane < 16) {
-          const int ca = lane >> 2, cb = lane & 3;
-          for (int k = 1; k < K - 1; ++k) {
-            const double* rb = Rb + (size_t)k * SR;
-#pragma unroll
-            for (int i = 0; i < NS; ++i) acc += rb[ca * NS + i] * rb[cb * NS + i];
+      const int ops[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+      block_reduce<14>(sp, ops, red);
+      if (tid == 0) {
+        // unpack: pairs (ca, cb>=ca) in the order generated above; cb == 4 is the rhs column
+        int q = 0;
+        for (int ca = 0; ca < 4; ++ca)
+          for (int cb = ca; cb < 5; ++cb) {
+            const double v = red[q++];
+            if (cb < 4) { gl[18 + ca * 4 + cb] -= v; if (cb != ca) gl[18 + cb * 4 + ca] -= v; }
+            else gl[34 + ca] -= v;
           }
-          gl[18 + lane] -= acc;
-        } else if (lane < 20) {
-          const int ca = lane - 16;
-          for (int k = 1; k < K - 1; ++k) {
-            const double* rb = Rb + (size_t)k * SR;
-#pragma unroll
-            for (int i = 0; i < NS; ++i) acc += rb[ca * NS + i] * dW[k * NSP + i];
-          }
-          gl[34 + ca] -= acc;
-        }
+        schur_factor_solve(gl + 18, gl + 34, gl + 4);
       }
-      __syncwarp();
-      // backward substitution: Y_k = Li' (V_k - Lo_k' Y_{k+1})
-      for (int k = K - 2; k >= 1; --k) {
-        const double* dk = Dk + (size_t)k * SD;
-        if (lane < 5 * NS) {
-          double r;
-          if (rc < 4) r = Rb[(size_t)k * SR + rc * NS + ri]; else r = dW[k * NSP + ri];
-          if (k < K - 2) {
-            const double* lo = Ek + (size_t)k * SD;
-            const double* vn = (rc < 4) ? (Rb + (size_t)(k + 1) * SR + rc * NS) : (dW + (k + 1) * NSP);
-#pragma unroll
-            for (int c = 0; c < NS; ++c) r -= lo[c * NS + ri] * vn[c];
-          }
-          red[32 + lane] = r;
-        }
-        __syncwarp();
-        if (lane < 5 * NS) {
-          double v = 0.0;
-#pragma unroll
-          for (int c = 0; c < NS; ++c) v += dk[c * NS + ri] * red[32 + rc * NS + c];
-          if (rc < 4) Rb[(size_t)k * SR + rc * NS + ri] = v; else dW[k * NSP + ri] = v;
-        }
-        __syncwarp();
-      }
-      // 4x4 Schur solve (Cholesky) on lane 0; keeps the factor in gl[18..33] for the corrector
-      if (lane == 0) {
-        double S[4][4];
-        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = gl[18 + i * 4 + j];
-        double tr = S[0][0] + S[1][1] + S[2][2] + S[3][3];
-        for (int j = 0; j < 4; ++j) {
-          double d = S[j][j] + 1e-14 * tr;
-          for (int c = 0; c < j; ++c) d -= S[j][c] * S[j][c];
-          if (!(d > 1e-300)) d = fmax(1e-10 * tr, 1e-300);
-          const double rs = rsqrt(d);
-          S[j][j] = d * rs;
-          for (int i = j + 1; i < 4; ++i) {
-            double v = S[i][j];
-            for (int c = 0; c < j; ++c) v -= S[i][c] * S[j][c];
-            S[i][j] = v * rs;
-          }
-        }
-        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) gl[18 + i * 4 + j] = S[i][j];
-        double y[4];
-        for (int i = 0; i < 4; ++i) { double v = gl[34 + i]; for (int c = 0; c < i; ++c) v -= S[i][c] * y[c]; y[i] = v / S[i][i]; }
-        for (int i = 3; i >= 0; --i) { double v = y[i]; for (int c = i + 1; c < 4; ++c) v -= S[c][i] * y[c]; y[i] = v / S[i][i]; }
-        for (int i = 0; i < 4; ++i) gl[4 + i] = y[i];
-      }
+      __syncthreads();
     }
-    __syncthreads();
+    cr_backward<Dm, 5>(Dk, Ek, Ck, Rb, dW, K - 2, tid, nthr);
     // dWa = v - Y dg_aff
     {
       const double g0 = gl[4], g1 = gl[5], g2 = gl[6], g3 = gl[7];
@@ -1034,14 +1214,14 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
           if (mode == 2) {
             const double* S = jac + NX * NX + 2 * NX * NU;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) { st[10 + i] = et[i]; prg -= et[i] * S[i]; }
+            for (int i = 0; i < NX; ++i) { ST2[(size_t)k * Dm::ST2 + i] = et[i]; prg -= et[i] * S[i]; }
             pr[5] -= stau;
           }
         }
         {
           double dx[NX];
 #pragma unroll
-          for (int i = 0; i < NX; ++i) dx[i] = w[i] - Wr[k * NSP + i];
+          for (int i = 0; i < NX; ++i) dx[i] = w[i] - WR(k, i);
           double stx = 0.0;
 #pragma unroll
           for (int e = 0; e < NEX; ++e) {
@@ -1065,7 +1245,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
             double f = -tu, fa = -ga3, fd = -gd3;
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
-              f += sgn(e, j) * (w[NX + j] - Wr[k * NSP + NX + j]); fa += sgn(e, j) * da[NX + j]; fd += sgn(e, j) * dz[NX + j];
+              f += sgn(e, j) * (w[NX + j] - WR(k, NX + j)); fa += sgn(e, j) * da[NX + j]; fd += sgn(e, j) * dz[NX + j];
             }
             double tau = 0.0;
             row(ws.sP + o, ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
@@ -1203,10 +1383,10 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
           double acc[NS], t[NS];
 #pragma unroll
           for (int i = 0; i < NS; ++i) acc[i] = dW[k * NSP + i];
-          JpT<Dm>(JAC + (size_t)k * NJ, ST + (size_t)k * STG + 10, t);
+          JpT<Dm>(JAC + (size_t)k * NJ, ST2 + (size_t)k * Dm::ST2, t);
 #pragma unroll
           for (int i = 0; i < NS; ++i) acc[i] += t[i];
-          JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ST + (size_t)(k - 1) * STG + 10, t);
+          JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ST2 + (size_t)(k - 1) * Dm::ST2, t);
 #pragma unroll
           for (int i = 0; i < NS; ++i) dW[k * NSP + i] = -(acc[i] + t[i]);
         }
@@ -1224,70 +1404,26 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
           for (int c = 0; c < 4; ++c) gl[34 + c] = -bg[c];
         }
         __syncthreads();
-        // corrector solve on warp 0: rg = bg - Y'b ; v = T^-1 b ; dg = S^-1 rg ; dW = v - Y dg
-        if (tid < 32) {
-          const int lane = tid;
-          if (lane < 4) {
-            double acc = 0.0;
-            for (int k = 1; k < K - 1; ++k) {
-              const double* rb = Rb + (size_t)k * SR;
+        // corrector solve (all threads): rg = bg - Y'b ; v = T^-1 b ; dg = S^-1 rg ; dW = v - Y dg
+        {
+          double yb[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int k = 1 + tid; k <= K - 2; k += nthr) {
+            const double* rb = Rb + (size_t)k * SR;
 #pragma unroll
-              for (int i = 0; i < NS; ++i) acc += rb[lane * NS + i] * dW[k * NSP + i];
-            }
-            gl[34 + lane] -= acc;
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int i = 0; i < NS; ++i) yb[c] += rb[c * NS + i] * dW[k * NSP + i];
           }
-          __syncwarp();
-          if (lane == 0) {
-            double S[4][4], y[4];
-            for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = gl[18 + i * 4 + j];
-            for (int i = 0; i < 4; ++i) { double v = gl[34 + i]; for (int c = 0; c < i; ++c) v -= S[i][c] * y[c]; y[i] = v / S[i][i]; }
-            for (int i = 3; i >= 0; --i) { double v = y[i]; for (int c = i + 1; c < 4; ++c) v -= S[c][i] * y[c]; y[i] = v / S[i][i]; }
-            for (int i = 0; i < 4; ++i) gl[8 + i] = y[i];
+          const int ops4[4] = {0, 0, 0, 0};
+          block_reduce<4>(yb, ops4, red);
+          if (tid == 0) {
+            for (int c = 0; c < 4; ++c) gl[34 + c] -= red[c];
+            schur_solve(gl + 18, gl + 34, gl + 8);
           }
-          __syncwarp();
-          // forward / backward substitution, single rhs, lanes 0..NS-1
-          for (int k = 1; k < K - 1; ++k) {
-            const double* dk = Dk + (size_t)k * SD;
-            if (lane < NS) {
-              double r = dW[k * NSP + lane];
-              if (k > 1) {
-                const double* lo = Ek + (size_t)(k - 1) * SD;
-#pragma unroll
-                for (int c = 0; c < NS; ++c) r -= lo[lane * NS + c] * dW[(k - 1) * NSP + c];
-              }
-              red[32 + lane] = r;
-            }
-            __syncwarp();
-            if (lane < NS) {
-              double v = 0.0;
-#pragma unroll
-              for (int c = 0; c < NS; ++c) v += dk[lane * NS + c] * red[32 + c];
-              dW[k * NSP + lane] = v;
-            }
-            __syncwarp();
-          }
-          for (int k = K - 2; k >= 1; --k) {
-            const double* dk = Dk + (size_t)k * SD;
-            if (lane < NS) {
-              double r = dW[k * NSP + lane];
-              if (k < K - 2) {
-                const double* lo = Ek + (size_t)k * SD;
-#pragma unroll
-                for (int c = 0; c < NS; ++c) r -= lo[c * NS + lane] * dW[(k + 1) * NSP + c];
-              }
-              red[32 + lane] = r;
-            }
-            __syncwarp();
-            if (lane < NS) {
-              double v = 0.0;
-#pragma unroll
-              for (int c = 0; c < NS; ++c) v += dk[c * NS + lane] * red[32 + c];
-              dW[k * NSP + lane] = v;
-            }
-            __syncwarp();
-          }
+          // (the barrier inside the first level of cr_forward orders these writes before any read of gl[8..11])
         }
-        __syncthreads();
+        cr_forward<Dm, 1>(Ek, Ck, Rb, dW, K - 2, tid, nthr);
+        cr_backward<Dm, 1>(Dk, Ek, Ck, Rb, dW, K - 2, tid, nthr);
         {
           const double g0 = gl[8], g1 = gl[9], g2 = gl[10], g3 = gl[11];
           for (int k = tid; k < K; k += nthr) {
@@ -1382,21 +1518,41 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas) {
   }
 }
 
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+// Two blocks per SM need <= (228 KB - 2 x 1 KB reserved) / 2 each; keep the Jacobians in shared memory only if that holds
+// or if the problem does not fit otherwise anyway.
+constexpr size_t SMEM_TWO_PER_SM = 113 * 1024;
+
 template <class M>
-size_t solver_smem_bytes(int K) {
+size_t solver_smem_bytes(int K, bool jac_in_smem) {
   using Dm = Dims<M>;
-  return ((size_t)K * Dm::PER_STAGE + Dm::SMALL) * sizeof(double);
+  return ((size_t)K * (jac_in_smem ? Dm::PER_STAGE : Dm::PER_STAGE_NOJAC) + Dm::SMALL) * sizeof(double);
+}
+template <class M>
+bool solver_jac_in_smem(int K) {
+  const size_t with = solver_smem_bytes<M>(K, true), without = solver_smem_bytes<M>(K, false);
+  if (with <= SMEM_TWO_PER_SM) return true;          // fits twice per SM either way
+  if (without <= SMEM_TWO_PER_SM) return false;      // dropping the Jacobians buys the second block
+  return with <= SMEM_LIMIT;                         // one block per SM: keep them on chip if possible
 }
 template <class M>
 size_t solver_ws_doubles_per_agent(int K, int NH) {
   using Dm = Dims<M>;
   return (size_t)K * (2 * Dm::NPLAIN + 5 * (size_t)NH);
 }
+template <class M>
+size_t solver_ws_total_doubles(int n_agents, int K, int NH) {
+  using Dm = Dims<M>;
+  size_t tot = solver_ws_doubles_per_agent<M>(K, NH) * (size_t)n_agents;
+  if (!solver_jac_in_smem<M>(K)) tot += (size_t)n_agents * K * Dm::NJ;
+  return tot;
+}
 
 template <class M>
 int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
-  const size_t smem = solver_smem_bytes<M>(a.K);
-  if (smem > 227 * 1024) {
+  const bool jac_smem = solver_jac_in_smem<M>(a.K);
+  const size_t smem = solver_smem_bytes<M>(a.K, jac_smem);
+  if (smem > SMEM_LIMIT) {
     snprintf(g_last_error, sizeof(g_last_error), "K=%d needs %zu B of shared memory per agent (> 227 KB)", a.K, smem);
     return SCVX_E_UNSUPPORTED;
   }
@@ -1405,7 +1561,8 @@ int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
   int threads = ((a.K + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > SOLVER_MAX_THREADS) threads = SOLVER_MAX_THREADS;
-  ipm_kernel<M><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9);
+  const size_t jac_off = solver_ws_doubles_per_agent<M>(a.K, a.M + a.n_nbr) * (size_t)a.n_agents;
+  ipm_kernel<M><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_smem ? 1 : 0, jac_off);
   SCVX_CHECK_LAUNCH("scvx_solve_batched");
   return SCVX_OK;
 }
@@ -1416,13 +1573,13 @@ using namespace scvx;
 
 extern "C" unsigned long long scvx_solve_workspace_bytes(int model_id, int n_agents, int K, int M, int n_nbr) {
   if (n_agents < 0 || K < 3 || M < 0 || n_nbr < 0) return 0ull;
-  size_t per;
+  size_t tot;
   switch (model_id) {
-    case SCVX_MODEL_UNICYCLE: per = solver_ws_doubles_per_agent<Unicycle>(K, M + n_nbr); break;
-    case SCVX_MODEL_SINGLE_INTEGRATOR: per = solver_ws_doubles_per_agent<SingleIntegrator>(K, M + n_nbr); break;
+    case SCVX_MODEL_UNICYCLE: tot = solver_ws_total_doubles<Unicycle>(n_agents, K, M + n_nbr); break;
+    case SCVX_MODEL_SINGLE_INTEGRATOR: tot = solver_ws_total_doubles<SingleIntegrator>(n_agents, K, M + n_nbr); break;
     default: return 0ull;
   }
-  return (unsigned long long)per * sizeof(double) * (unsigned long long)n_agents;
+  return (unsigned long long)tot * sizeof(double);
 }
 
 extern "C" int scvx_solve_batched(const scvx_solve_args* a, void* stream) {

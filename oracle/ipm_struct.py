@@ -33,9 +33,37 @@ def _signs(n):
     return np.array(list(itertools.product([1.0, -1.0], repeat=n)))[:, ::-1].copy()   # bit i of e -> sign of comp i
 
 
+def spd_inverse_frozen(Dj, piv_tol=1e-12):
+    """Inverse of an SPD block through its Cholesky factor, the way the kernel does it in registers: a pivot that has
+    lost all significance (d <= piv_tol * original diagonal) is FROZEN -- its reciprocal is set to 0, which removes
+    that row/column from the step instead of injecting round-off noise.  Returns Li (inverse factor), Dinv = Li'Li."""
+    ns = Dj.shape[0]
+    L = np.zeros((ns, ns)); dinv = np.zeros(ns)
+    reg = 1e-13 * np.trace(Dj) / ns
+    for j in range(ns):
+        d0 = Dj[j, j] + reg
+        d = d0 - (L[j, :j] ** 2).sum()
+        if not (d > piv_tol * d0):
+            dinv[j] = 0.0
+            L[j, j] = 0.0
+            L[j + 1:, j] = 0.0
+            continue
+        rs = 1.0 / np.sqrt(d)
+        dinv[j] = rs
+        L[j, j] = d * rs
+        for i in range(j + 1, ns):
+            L[i, j] = (Dj[i, j] - (L[i, :j] * L[j, :j]).sum()) * rs
+    Li = np.zeros((ns, ns))
+    for j in range(ns):
+        Li[j, j] = dinv[j]
+        for i in range(j + 1, ns):
+            Li[i, j] = -(L[i, j:i] * Li[j:i, j]).sum() * dinv[i]
+    return Li, Li.T @ Li
+
+
 class StructIPM:
-    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False):
-        self.p, self.verbose = p, verbose
+    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False, linalg="cr"):
+        self.p, self.verbose, self.linalg = p, verbose, linalg
         self.mu0, self.max_iter, self.eps_gap, self.eps_feas = mu0, max_iter, eps_gap, eps_feas
         m, K = p.model, p.K
         self.K, self.nx, self.nu, self.d = K, m.n_x, m.n_u, m.d
@@ -306,31 +334,89 @@ class StructIPM:
         for k in (0, K - 1):
             D[k] = np.eye(ns); Bd[k] = 0.0
         E[0] = 0.0; E[K - 2] = 0.0
-        # block Cholesky
-        Lk = np.zeros((K, ns, ns)); Li = np.zeros((K, ns, ns)); Lo = np.zeros((K - 1, ns, ns))
-        ok = True
-        for k in range(K):
-            Dk = D[k] - (Lo[k - 1] @ Lo[k - 1].T if k > 0 else 0.0)
-            Dk = Dk + 1e-13 * np.trace(Dk) / ns * np.eye(ns)
-            try:
-                Lk[k] = np.linalg.cholesky(Dk)
-            except np.linalg.LinAlgError:
-                ok = False
-                Lk[k] = np.linalg.cholesky(Dk + 1e-8 * np.trace(np.abs(Dk)) * np.eye(ns))
-            Li[k] = np.linalg.inv(Lk[k])
-            if k < K - 1:
-                Lo[k] = E[k] @ Li[k].T
-        fac = {"Li": Li, "Lo": Lo, "Bd": Bd, "Gg": Gg, "ok": ok}
+        if self.linalg == "cr":
+            fac = {"Bd": Bd, "Gg": Gg, "ok": True}
+            fac.update(self._cr_factor(D[1:K - 1].copy(), E[1:K - 2].copy()))
+        else:
+            # sequential block Cholesky (the first kernel version)
+            Lk = np.zeros((K, ns, ns)); Li = np.zeros((K, ns, ns)); Lo = np.zeros((K - 1, ns, ns))
+            ok = True
+            for k in range(K):
+                Dk = D[k] - (Lo[k - 1] @ Lo[k - 1].T if k > 0 else 0.0)
+                Li[k], _ = spd_inverse_frozen(Dk)
+                if k < K - 1:
+                    Lo[k] = E[k] @ Li[k].T
+            fac = {"Li": Li, "Lo": Lo, "Bd": Bd, "Gg": Gg, "ok": ok}
         # Y = T^-1 B' (4 rhs) and the Schur complement
         Y = self._tsolve(fac, Bd)
         fac["Y"] = Y
         fac["S"] = Gg - np.einsum("kia,kib->ab", Bd, Y)
         return fac
 
+    # ---- block cyclic reduction over the free stages (the kernel's factorisation) ---------------------------
+    def _cr_factor(self, D, Lc):
+        """D: (n, ns, ns) diagonal blocks of the free stages, Lc: (n-1, ns, ns) with Lc[i] = T[i+1, i].
+        Odd-even elimination with stride s = 1, 2, 4, ...; positions are 1-based (p = index + 1): at stride s the
+        nodes p = s, 3s, 5s, ... are eliminated.  Stored per node: Dinv, P = Dinv T[j, left], Q = Dinv T[j, right]."""
+        n, ns = D.shape[0], self.ns
+        Lm = np.zeros((n, ns, ns))
+        Lm[1:] = Lc                       # Lm[i] = coupling of node i to its current LEFT neighbour
+        Dinv = np.zeros_like(D); P = np.zeros_like(D); Q = np.zeros_like(D)
+        s = 1
+        while s <= n:
+            odd = [p - 1 for p in range(s, n + 1, 2 * s)]
+            keepL = {}
+            for j in odd:                                         # phase 1: invert, P, Q, push-left
+                a, b = j - s, j + s
+                Li, _ = spd_inverse_frozen(D[j])
+                Dinv[j] = Li                       # the inverse FACTOR is stored; D^-1 v is applied as Li'(Li v)
+                Lj = Lm[j].copy() if a >= 0 else np.zeros((ns, ns))
+                P[j] = Li.T @ (Li @ Lj)
+                Q[j] = Li.T @ (Li @ Lm[b].T) if b < n else np.zeros((ns, ns))
+                if a >= 0:
+                    D[a] -= Lj.T @ P[j]
+            for j in odd:                                         # phase 2: push-right, new left coupling of b
+                b = j + s
+                if b < n:
+                    D[b] -= Lm[b] @ Q[j]
+                    Lm[b] = -Lm[b] @ P[j]
+            s *= 2
+        return {"Dinv": Dinv, "P": P, "Q": Q}
+
+    def _cr_solve(self, fac, R):
+        """Solve T V = R for R (n, ns, nrhs) with the cyclic-reduction factor."""
+        Dinv, P, Q = fac["Dinv"], fac["P"], fac["Q"]
+        n = R.shape[0]
+        V = R.copy()
+        strides = []
+        s = 1
+        while s <= n:
+            strides.append(s)
+            for p in range(2 * s, n + 1, 2 * s):                  # even nodes pull from their odd neighbours
+                a = p - 1
+                V[a] -= Q[a - s].T @ V[a - s]
+                if a + s < n:
+                    V[a] -= P[a + s].T @ V[a + s]
+            s *= 2
+        for s in reversed(strides):
+            for p in range(s, n + 1, 2 * s):
+                j = p - 1
+                x = Dinv[j].T @ (Dinv[j] @ V[j])
+                if j - s >= 0:
+                    x -= P[j] @ V[j - s]
+                if j + s < n:
+                    x -= Q[j] @ V[j + s]
+                V[j] = x
+        return V
+
     def _tsolve(self, fac, R):
-        """Solve T V = R for R (K, ns, nrhs) with the block-Cholesky factor."""
-        Li, Lo = fac["Li"], fac["Lo"]
+        """Solve T V = R for R (K, ns, nrhs) (fixed stages 0 and K-1 are identity rows)."""
         K = self.K
+        if self.linalg == "cr":
+            V = R.copy()
+            V[1:K - 1] = self._cr_solve(fac, R[1:K - 1])
+            return V
+        Li, Lo = fac["Li"], fac["Lo"]
         V = np.zeros_like(R)
         for k in range(K):
             r = R[k] - (Lo[k - 1] @ V[k - 1] if k > 0 else 0.0)
