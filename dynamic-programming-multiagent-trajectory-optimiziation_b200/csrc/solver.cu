@@ -1151,33 +1151,35 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
     // ------------------------------------------------------------------------------------ MODE 1/2/3/4
     // A generic visitor over all rows of stage k.  For each row it provides (s, lambda, r_p, g.dz_aff, g.dz) and
     // the address where the row state lives; F does the mode-specific work.
-    auto max_step = [](double v, double dv, double a) -> double { return (dv < 0.0) ? fmin(a, -v / dv) : a; };
-
     for (int mode = 1; mode <= 4; ++mode) {
       const double sigmu = gl[43];
       const double al_p = gl[41], al_d = gl[42];
       double pr[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) pr[i] = 0.0;
-      pr[0] = 1.0; pr[1] = 1.0;
       // pr: 0 alpha_p (min), 1 alpha_d (min), 2 sum ds*l, 3 sum s*dl, 4 sum ds*dl, 5..7 corrector bg pieces (t_nu, t_x, t_u), 8.. see below
       double prg = 0.0;   // sigma-column piece of the corrector bg
       const double ga0 = gl[4], ga1 = gl[5], ga2 = gl[6], ga3 = gl[7];     // affine global step
       const double gd0 = gl[8], gd1 = gl[9], gd2 = gl[10], gd3 = gl[11];   // final global step
+      // Step-length ratios without divisions: the primal ratio -ds/s reuses the row's reciprocal 1/s; the dual ratio
+      // -dl/l is tracked as a fraction (qdn/qdd) compared by cross-multiplication.  alpha = min(1, 1/max ratio).
+      double qp = 0.0, qdn = 0.0, qdd = 1.0;
+      auto upd_d = [&](double dl, double l) { if (-dl * qdd > qdn * l) { qdn = -dl; qdd = l; } };
       // per-row kernel: returns tau (mode 2) and updates statistics / state
       auto row = [&](double* ps, double* pl, double gz_h, double gdza, double gdz, double& tau_out) {
         const double s = *ps, l = *pl;
-        const double rp = gz_h + s, wgt = l / s;
+        const double rs = __drcp_rn(s);
+        const double rp = gz_h + s, wgt = l * rs;
         const double dsa = -rp - gdza, dla = -l - wgt * dsa;
         if (mode == 1) {
-          pr[0] = max_step(s, dsa, pr[0]); pr[1] = max_step(l, dla, pr[1]);
+          qp = fmax(qp, -dsa * rs); upd_d(dla, l);
           pr[2] += dsa * l; pr[3] += s * dla; pr[4] += dsa * dla;
           return;
         }
         const double c2 = dsa * dla;
-        if (mode == 2) { tau_out = (sigmu - c2 + l * rp) / s; return; }
-        const double ds = -rp - gdz, dl = -l + (sigmu - c2) / s - wgt * ds;
-        if (mode == 3) { pr[0] = max_step(s, ds, pr[0]); pr[1] = max_step(l, dl, pr[1]); return; }
+        if (mode == 2) { tau_out = (sigmu - c2 + l * rp) * rs; return; }
+        const double ds = -rp - gdz, dl = -l + (sigmu - c2) * rs - wgt * ds;
+        if (mode == 3) { qp = fmax(qp, -ds * rs); upd_d(dl, l); return; }
         *ps = s + al_p * ds; *pl = l + al_d * dl;
       };
 
@@ -1300,34 +1302,33 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
             const double xi = ws.xi[o], s1 = ws.s1[o], s2 = ws.s2[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
             const double viol = hinge_b(h, k) - ap;
             const double r1 = viol - xi + s1, r2 = -xi + s2;
-            const double w1 = l1 / s1, w2 = l2 / s2;
+            const double rs1 = __drcp_rn(s1), rs2 = __drcp_rn(s2);
+            const double w1 = l1 * rs1, w2 = l2 * rs2, rw = __drcp_rn(w1 + w2);
             // affine step of this hinge pair (sigmu = 0, c = 0)
             const double t1a = w1 * r1, t2a = w2 * r2;
             const double rxa = -hw + t1a + t2a;
-            const double dxia = (rxa - w1 * ada) / (w1 + w2);
+            const double dxia = (rxa - w1 * ada) * rw;
             const double ds1a = -r1 + ada + dxia, ds2a = -r2 + dxia;
             const double dl1a = -l1 - w1 * ds1a, dl2a = -l2 - w2 * ds2a;
             if (mode == 1) {
-              pr[0] = max_step(s1, ds1a, pr[0]); pr[0] = max_step(s2, ds2a, pr[0]);
-              pr[1] = max_step(l1, dl1a, pr[1]); pr[1] = max_step(l2, dl2a, pr[1]);
+              qp = fmax(qp, fmax(-ds1a * rs1, -ds2a * rs2)); upd_d(dl1a, l1); upd_d(dl2a, l2);
               pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += ds1a * dl1a + ds2a * dl2a;
               continue;
             }
             const double c1 = ds1a * dl1a, c2 = ds2a * dl2a;
-            const double t1 = (sigmu - c1 + l1 * r1) / s1, t2 = (sigmu - c2 + l2 * r2) / s2;
+            const double t1 = (sigmu - c1 + l1 * r1) * rs1, t2 = (sigmu - c2 + l2 * r2) * rs2;
             const double rhs_xi = -hw + t1 + t2;
             if (mode == 2) {
-              const double th = t1 - w1 * rhs_xi / (w1 + w2);
+              const double th = t1 - w1 * rhs_xi * rw;
 #pragma unroll
               for (int c = 0; c < D; ++c) bt[c] -= av[c] * th;
               continue;
             }
-            const double dxi = (rhs_xi - w1 * adz) / (w1 + w2);
+            const double dxi = (rhs_xi - w1 * adz) * rw;
             const double ds1 = -r1 + adz + dxi, ds2 = -r2 + dxi;
-            const double dl1 = -l1 + (sigmu - c1) / s1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) / s2 - w2 * ds2;
+            const double dl1 = -l1 + (sigmu - c1) * rs1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) * rs2 - w2 * ds2;
             if (mode == 3) {
-              pr[0] = max_step(s1, ds1, pr[0]); pr[0] = max_step(s2, ds2, pr[0]);
-              pr[1] = max_step(l1, dl1, pr[1]); pr[1] = max_step(l2, dl2, pr[1]);
+              qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
               continue;
             }
             ws.xi[o] = xi + al_p * dxi; ws.s1[o] = s1 + al_p * ds1; ws.s2[o] = s2 + al_p * ds2;
@@ -1347,12 +1348,15 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         }
       }
       // ---- mode epilogues
+      auto max_step = [](double v, double dv, double a) -> double { return (dv < 0.0) ? fmin(a, -v / dv) : a; };
+      pr[0] = qp; pr[1] = qdn / qdd;            // max ratios of this thread's rows
       if (mode == 1) {
-        const int ops[5] = {1, 1, 0, 0, 0};
+        const int ops[5] = {2, 2, 0, 0, 0};
         block_reduce<5>(pr, ops, red);
         if (tid == 0) {
           // global rows
-          double ap = red[0], ad = red[1], s2l = red[2], sdl = red[3], dd = red[4];
+          double ap = (red[0] > 1.0) ? 1.0 / red[0] : 1.0, ad = (red[1] > 1.0) ? 1.0 / red[1] : 1.0;
+          double s2l = red[2], sdl = red[3], dd = red[4];
           const double gG[3][4] = {{1, 0, 1, 1}, {-1, 0, 1, 1}, {-1, 0, 0, 0}};
           for (int r = 0; r < 3; ++r) {
             const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r], wgt = l / s;
@@ -1390,7 +1394,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
           for (int i = 0; i < NS; ++i) dW[k * NSP + i] = -(acc[i] + t[i]);
         }
-        const int ops[8] = {1, 1, 0, 0, 0, 0, 0, 0};
+        const int ops[8] = {2, 2, 0, 0, 0, 0, 0, 0};
         block_reduce<8>(pr, ops, red);
         if (tid == 0) {
           double bg[4] = {red[4], red[5], red[6], red[7]};
@@ -1436,10 +1440,10 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         }
         __syncthreads();
       } else if (mode == 3) {
-        const int ops[2] = {1, 1};
+        const int ops[2] = {2, 2};
         block_reduce<2>(pr, ops, red);
         if (tid == 0) {
-          double ap = red[0], ad = red[1];
+          double ap = (red[0] > 1.0) ? 1.0 / red[0] : 1.0, ad = (red[1] > 1.0) ? 1.0 / red[1] : 1.0;
           const double gG[3][4] = {{1, 0, 1, 1}, {-1, 0, 1, 1}, {-1, 0, 0, 0}};
           for (int r = 0; r < 3; ++r) {
             const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r], wgt = l / s;
