@@ -33,13 +33,13 @@ def _signs(n):
     return np.array(list(itertools.product([1.0, -1.0], repeat=n)))[:, ::-1].copy()   # bit i of e -> sign of comp i
 
 
-def spd_inverse_frozen(Dj, piv_tol=1e-12):
+def spd_inverse_frozen(Dj, piv_tol=1e-12, reg_rel=0.0):
     """Inverse of an SPD block through its Cholesky factor, the way the kernel does it in registers: a pivot that has
     lost all significance (d <= piv_tol * original diagonal) is FROZEN -- its reciprocal is set to 0, which removes
     that row/column from the step instead of injecting round-off noise.  Returns Li (inverse factor), Dinv = Li'Li."""
     ns = Dj.shape[0]
     L = np.zeros((ns, ns)); dinv = np.zeros(ns)
-    reg = 1e-13 * np.trace(Dj) / ns
+    reg = reg_rel * np.trace(Dj) / ns
     for j in range(ns):
         d0 = Dj[j, j] + reg
         d = d0 - (L[j, :j] ** 2).sum()
@@ -62,8 +62,9 @@ def spd_inverse_frozen(Dj, piv_tol=1e-12):
 
 
 class StructIPM:
-    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False, linalg="cr"):
+    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False, linalg="cr", step_frac=0.999, uncapped=False):
         self.p, self.verbose, self.linalg = p, verbose, linalg
+        self.step_frac, self.uncapped = step_frac, uncapped
         self.mu0, self.max_iter, self.eps_gap, self.eps_feas = mu0, max_iter, eps_gap, eps_feas
         m, K = p.model, p.K
         self.K, self.nx, self.nu, self.d = K, m.n_x, m.n_u, m.d
@@ -195,6 +196,14 @@ class StructIPM:
             if gap_ok and rp_inf <= self.eps_feas and rd_inf <= (1e-5 if deep else 1e-7) * (1.0 + cmax):
                 status = 0
                 break
+            # stall rule: when the optimum is tiny in scaled cost units the relative gap target sits below what fp64
+            # can deliver (mu stalls around 1e-11); once the gap is below 1e-7 (1 + |obj|) and stops shrinking (or the
+            # dual residual blows up) the current -- primal feasible -- iterate is accepted.
+            if it > 0 and comp <= 1e-7 * (1.0 + abs(obj)) and rp_inf <= self.eps_feas and \
+                    (comp > 0.5 * comp_prev or (rd_inf > 10.0 * rd_prev and rd_inf > 1e-8 * (1.0 + cmax))):
+                status = 0
+                break
+            comp_prev, rd_prev = comp, rd_inf
             if not np.isfinite(mu):
                 status = 2
                 break
@@ -238,8 +247,8 @@ class StructIPM:
             S = (sN, sX, sU, sG, sP, sV, s1, s2); L = (lN, lX, lU, lG, lP, lV, l1, l2)
             masks = (None, None, None, None, fm, fm, hfree, hfree)
 
-            def maxstep(vals, dvals):
-                a = 1.0
+            def maxstep(vals, dvals, cap=1.0):
+                a = cap
                 for v, dv, mk in zip(vals, dvals, masks):
                     neg = dv < 0
                     if mk is not None:
@@ -258,14 +267,17 @@ class StructIPM:
             sg = (comp_aff / comp) ** 3
             cc = [dv * dl_ for dv, dl_ in zip(dS, dL)]
             dW, dg, dxi, dS, dL = newton(sg * mu, *cc)
-            ap, ad = maxstep(S, dS), maxstep(L, dL)
+            cap = 1e300 if self.uncapped else 1.0
+            ap, ad = maxstep(S, dS, cap), maxstep(L, dL, cap)
             if self.qrho > 0 or self.ball:
                 ap = ad = min(ap, ad)
-            ap, ad = min(1.0, 0.99 * ap), min(1.0, 0.99 * ad)
+            ap, ad = min(1.0, self.step_frac * ap), min(1.0, self.step_frac * ad)
             W = W + ap * dW; sig += ap * dg[0]; t_nu += ap * dg[1]; t_x += ap * dg[2]; t_u += ap * dg[3]
-            xi = xi + ap * dxi
-            sN, sX, sU, sG, sP, sV, s1, s2 = [v + ap * dv for v, dv in zip(S, dS)]
-            lN, lX, lU, lG, lP, lV, l1, l2 = [l + ad * dl_ for l, dl_ in zip(L, dL)]
+            xi = xi + ap * np.where(hfree, dxi, 0.0)
+            # rows of the fixed stages are placeholders (the kernel never touches them): keep them frozen
+            upd = lambda v, dv, a, mk: v + a * (dv if mk is None else np.where(np.broadcast_to(mk, dv.shape), dv, 0.0))   # noqa: E731
+            sN, sX, sU, sG, sP, sV, s1, s2 = [upd(v, dv, ap, mk) for v, dv, mk in zip(S, dS, masks)]
+            lN, lX, lU, lG, lP, lV, l1, l2 = [upd(l, dl_, ad, mk) for l, dl_, mk in zip(L, dL, masks)]
         X = W[:, :nx].T.copy(); U = W[:, nx:].T.copy()
         return {"X": X, "U": U, "sigma": float(sig), "iters": it, "status": status, "t": (t_nu, t_x, t_u)}
 
