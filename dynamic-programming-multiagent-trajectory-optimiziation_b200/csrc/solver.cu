@@ -28,6 +28,9 @@
 namespace scvx {
 
 constexpr int SOLVER_MAX_THREADS = 256;
+// Slacks are NOT stored: every plain row is linear and the start is strictly feasible, so s = h - G z is recomputed from
+// the iterate in every pass (halves the row-state traffic and keeps s consistent with z to round-off).
+constexpr double TINY_S = 1e-14;
 
 // ---- small helpers ------------------------------------------------------------------------------
 __device__ __forceinline__ double wsum(double v) {
@@ -91,8 +94,9 @@ struct Dims {
 __device__ __forceinline__ double sgn(int e, int i) { return ((e >> i) & 1) ? -1.0 : 1.0; }
 
 struct AgentPtrs {
-  double *sP, *lP;                     // [NPLAIN][K]
-  double *xi, *s1, *s2, *l1, *l2;      // [NH][K]
+  double *lP;                          // [NPLAIN][K]  multipliers of the plain rows
+  double *sB;                          // [K]          stored slack of the (nonlinear) ball row, single integrator only
+  double *xi, *l1, *l2;                // [NH][K]      hinge slack and the two multipliers of each hinge pair
 };
 
 // ---- per-stage linear forms ----------------------------------------------------------------------
@@ -462,32 +466,31 @@ __device__ __forceinline__ void cr_backward(const double* A, const double* B, co
   }
 }
 
-// 4x4 Schur complement: Cholesky in place (kept for the corrector), then solve.
-__device__ __forceinline__ void schur_solve(const double* Sf, const double* rhs, double* out) {
-  double y[4];
-  for (int i = 0; i < 4; ++i) { double v = rhs[i]; for (int c = 0; c < i; ++c) v -= Sf[i * 4 + c] * y[c]; y[i] = v / Sf[i * 4 + i]; }
-  for (int i = 3; i >= 0; --i) { double v = y[i]; for (int c = i + 1; c < 4; ++c) v -= Sf[c * 4 + i] * y[c]; y[i] = v / Sf[i * 4 + i]; }
-  for (int i = 0; i < 4; ++i) out[i] = y[i];
-}
-__device__ __forceinline__ void schur_factor_solve(double* Sm, const double* rhs, double* out) {
-  double S[4][4];
-  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) S[i][j] = Sm[i * 4 + j];
-  const double tr = S[0][0] + S[1][1] + S[2][2] + S[3][3];
-  for (int j = 0; j < 4; ++j) {
-    double d = S[j][j] + 1e-14 * tr;
-    for (int c = 0; c < j; ++c) d -= S[j][c] * S[j][c];
-    if (!(d > 1e-300)) d = fmax(1e-10 * tr, 1e-300);
-    const double rs = rsqrt(d);
-    S[j][j] = d * rs;
-    for (int i = j + 1; i < 4; ++i) {
-      double v = S[i][j];
-      for (int c = 0; c < j; ++c) v -= S[i][c] * S[j][c];
-      S[i][j] = v * rs;
+// 4x4 Schur complement of the border (sigma, t_nu, t_x, t_u): Gaussian elimination with partial pivoting, redone for
+// every right-hand side (the matrix is kept, the cost is nil).  An unpivoted Cholesky produced non-finite steps on
+// late, nearly singular iterates where LAPACK's pivoted LU (the CPU twin) sails through.
+__device__ __forceinline__ void schur_solve(const double* Sm, const double* rhs, double* out) {
+  double A[4][5];
+  for (int i = 0; i < 4; ++i) { for (int j = 0; j < 4; ++j) A[i][j] = Sm[i * 4 + j]; A[i][4] = rhs[i]; }
+  for (int c = 0; c < 4; ++c) {
+    int piv = c;
+    double best = fabs(A[c][c]);
+    for (int r = c + 1; r < 4; ++r) if (fabs(A[r][c]) > best) { best = fabs(A[r][c]); piv = r; }
+    if (piv != c) for (int j = 0; j < 5; ++j) { const double t = A[c][j]; A[c][j] = A[piv][j]; A[piv][j] = t; }
+    const double d = (best > 1e-300) ? A[c][c] : 1e-300;
+    for (int r = c + 1; r < 4; ++r) {
+      const double f = A[r][c] / d;
+      for (int j = c; j < 5; ++j) A[r][j] -= f * A[c][j];
     }
+    A[c][c] = d;
   }
-  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) Sm[i * 4 + j] = S[i][j];
-  schur_solve(Sm, rhs, out);
+  for (int i = 3; i >= 0; --i) {
+    double v = A[i][4];
+    for (int j = i + 1; j < 4; ++j) v -= A[i][j] * out[j];
+    out[i] = v / A[i][i];
+  }
 }
+__device__ __forceinline__ void schur_factor_solve(double* Sm, const double* rhs, double* out) { schur_solve(Sm, rhs, out); }
 
 // ---- the kernel -----------------------------------------------------------------------------------
 template <class M>
@@ -537,10 +540,10 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 
   AgentPtrs ws;
   {
-    double* base = (double*)a.workspace + (size_t)agent * ((size_t)K * (2 * NPLAIN + 5 * NH));
-    ws.sP = base; ws.lP = ws.sP + (size_t)NPLAIN * K;
-    ws.xi = ws.lP + (size_t)NPLAIN * K; ws.s1 = ws.xi + (size_t)NH * K; ws.s2 = ws.s1 + (size_t)NH * K;
-    ws.l1 = ws.s2 + (size_t)NH * K; ws.l2 = ws.l1 + (size_t)NH * K;
+    double* base = (double*)a.workspace + (size_t)agent * ((size_t)K * (NPLAIN + 3 * NH + (BALL ? 1 : 0)));
+    ws.lP = base;
+    ws.xi = ws.lP + (size_t)NPLAIN * K; ws.l1 = ws.xi + (size_t)NH * K; ws.l2 = ws.l1 + (size_t)NH * K;
+    ws.sB = ws.l2 + (size_t)NH * K;
   }
   auto hinge_a = [&](int h, int c, int k) -> double {
     return (h < Mobs) ? obs_a[((size_t)h * D + c) * K + k] : col_a[((size_t)(h - Mobs) * D + c) * K + k];
@@ -654,7 +657,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
         for (int i = 0; i < NX; ++i) f += sgn(e, i) * nu[i];
         const double s = fmax(-f, 1e-8);
-        ws.sP[(size_t)(Dm::R_NU + e) * K + k] = s; ws.lP[(size_t)(Dm::R_NU + e) * K + k] = mu0 / s;
+        ws.lP[(size_t)(Dm::R_NU + e) * K + k] = mu0 / s;
       }
     }
 #pragma unroll
@@ -663,7 +666,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
       for (int i = 0; i < NX; ++i) f += sgn(e, i) * (w[i] - WR(k, i));
       const double s = fmax(-f, 1e-8);
-      ws.sP[(size_t)(Dm::R_X + e) * K + k] = s; ws.lP[(size_t)(Dm::R_X + e) * K + k] = mu0 / s;
+      ws.lP[(size_t)(Dm::R_X + e) * K + k] = mu0 / s;
     }
 #pragma unroll
     for (int e = 0; e < NEU; ++e) {
@@ -671,29 +674,29 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
       for (int j = 0; j < NU; ++j) f += sgn(e, j) * (w[NX + j] - WR(k, NX + j));
       const double s = fmax(-f, 1e-8);
-      ws.sP[(size_t)(Dm::R_U + e) * K + k] = s; ws.lP[(size_t)(Dm::R_U + e) * K + k] = mu0 / s;
+      ws.lP[(size_t)(Dm::R_U + e) * K + k] = mu0 / s;
     }
     if (fr) {
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double s = fmax(sc.pos_hi - w[i], 1e-8);
-        ws.sP[(size_t)(Dm::R_P + i) * K + k] = s; ws.lP[(size_t)(Dm::R_P + i) * K + k] = mu0 / s;
+        ws.lP[(size_t)(Dm::R_P + i) * K + k] = mu0 / s;
         s = fmax(w[i] - sc.pos_lo, 1e-8);
-        ws.sP[(size_t)(Dm::R_P + D + i) * K + k] = s; ws.lP[(size_t)(Dm::R_P + D + i) * K + k] = mu0 / s;
+        ws.lP[(size_t)(Dm::R_P + D + i) * K + k] = mu0 / s;
       }
       if (!BALL) {
         const double sv[4] = {sc.v_max - w[NX], w[NX], sc.w_max - w[NX + 1], sc.w_max + w[NX + 1]};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const double s = fmax(sv[r], 1e-8);
-          ws.sP[(size_t)(Dm::R_V + r) * K + k] = s; ws.lP[(size_t)(Dm::R_V + r) * K + k] = mu0 / s;
+          ws.lP[(size_t)(Dm::R_V + r) * K + k] = mu0 / s;
         }
       } else {
         double n2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
         const double s = fmax(0.5 * (sc.v_max * sc.v_max - n2), 1e-8);
-        ws.sP[(size_t)Dm::R_V * K + k] = s; ws.lP[(size_t)Dm::R_V * K + k] = mu0 / s;
+        ws.sB[k] = s; ws.lP[(size_t)Dm::R_V * K + k] = mu0 / s;
       }
       for (int h = 0; h < NH; ++h) {
         if (!hinge_on(h)) continue;
@@ -705,7 +708,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         const double num = (viol >= 0.0) ? hw * viol + disc : 4.0 * mu0 * mu0 / fmax(disc - hw * viol, 1e-300);
         const double xi = (num + 2.0 * mu0) / (2.0 * hw);
         const size_t o = (size_t)h * K + k;
-        ws.xi[o] = xi; ws.s2[o] = xi; ws.s1[o] = xi - viol; ws.l1[o] = mu0 / (xi - viol); ws.l2[o] = mu0 / xi;
+        ws.xi[o] = xi; ws.l1[o] = mu0 / (xi - viol); ws.l2[o] = mu0 / xi;
       }
     }
   }
@@ -748,11 +751,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
         for (int e = 0; e < NEX; ++e) {
           const size_t o = (size_t)(Dm::R_NU + e) * K + k;
-          const double s = ws.sP[o], l = ws.lP[o];
+          const double l = ws.lP[o];
           double f = -tnu;
 #pragma unroll
           for (int i = 0; i < NX; ++i) f += sgn(e, i) * nu[i];
-          const double rp = f + s, wgt = l * __drcp_rn(s), tau = wgt * rp;
+          const double s = fmax(-f, TINY_S), rp = 0.0, wgt = l * __drcp_rn(s), tau = 0.0;
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           sw += wgt; stau += tau; slam += l;
 #pragma unroll
@@ -796,11 +799,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
         for (int e = 0; e < NEX; ++e) {
           const size_t o = (size_t)(Dm::R_X + e) * K + k;
-          const double s = ws.sP[o], l = ws.lP[o];
+          const double l = ws.lP[o];
           double f = -tx;
 #pragma unroll
           for (int i = 0; i < NX; ++i) f += sgn(e, i) * dx[i];
-          const double rp = f + s, wgt = l * __drcp_rn(s), tau = wgt * rp;
+          const double s = fmax(-f, TINY_S), rp = 0.0, wgt = l * __drcp_rn(s), tau = 0.0;
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           swx += wgt; stx += tau; slx += l;
 #pragma unroll
@@ -822,11 +825,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
         for (int e = 0; e < NEU; ++e) {
           const size_t o = (size_t)(Dm::R_U + e) * K + k;
-          const double s = ws.sP[o], l = ws.lP[o];
+          const double l = ws.lP[o];
           double f = -tu;
 #pragma unroll
           for (int j = 0; j < NU; ++j) f += sgn(e, j) * du[j];
-          const double rp = f + s, wgt = l * __drcp_rn(s), tau = wgt * rp;
+          const double s = fmax(-f, TINY_S), rp = 0.0, wgt = l * __drcp_rn(s), tau = 0.0;
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           swu += wgt; stu += tau; slu += l;
 #pragma unroll
@@ -845,11 +848,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           size_t o = (size_t)(Dm::R_P + i) * K + k;
-          double s = ws.sP[o], l = ws.lP[o], rp = (w[i] - sc.pos_hi) + s, wgt = l * __drcp_rn(s);
+          double l = ws.lP[o], s = fmax(sc.pos_hi - w[i], TINY_S), rp = 0.0, wgt = l * __drcp_rn(s);
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           Dl[i][i] += wgt; bt[i] += wgt * rp; bl[i] += l;
           o = (size_t)(Dm::R_P + D + i) * K + k;
-          s = ws.sP[o]; l = ws.lP[o]; rp = (sc.pos_lo - w[i]) + s; wgt = l * __drcp_rn(s);
+          l = ws.lP[o]; s = fmax(w[i] - sc.pos_lo, TINY_S); rp = 0.0; wgt = l * __drcp_rn(s);
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           Dl[i][i] += wgt; bt[i] -= wgt * rp; bl[i] -= l;
         }
@@ -858,7 +861,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const size_t o = (size_t)(Dm::R_V + r) * K + k;
-            const double s = ws.sP[o], l = ws.lP[o], rp = gz[r] + s, wgt = l * __drcp_rn(s);
+            const double l = ws.lP[o], s = fmax(-gz[r], TINY_S), rp = 0.0, wgt = l * __drcp_rn(s);
             const int c = NX + (r >> 1);
             const double sg = (r & 1) ? -1.0 : 1.0;
             part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
@@ -866,11 +869,12 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
           }
         } else {
           const size_t o = (size_t)Dm::R_V * K + k;
-          const double s = ws.sP[o], l = ws.lP[o];
+          const double l = ws.lP[o];
           double n2 = 0.0;
 #pragma unroll
           for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
-          const double rp = 0.5 * (n2 - sc.v_max * sc.v_max) + s, wgt = l * __drcp_rn(s);
+          // the ball row is quadratic: its slack stays an independent (stored) variable, rp = c(u) + s
+          const double s = ws.sB[k], rp = 0.5 * (n2 - sc.v_max * sc.v_max) + s, wgt = l * __drcp_rn(s);
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
 #pragma unroll
           for (int i = 0; i < NU; ++i) {
@@ -887,9 +891,9 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
           for (int c = 0; c < D; ++c) { av[c] = hinge_a(h, c, k); ap += av[c] * w[c]; }
           const size_t o = (size_t)h * K + k;
-          const double xi = ws.xi[o], s1 = ws.s1[o], s2 = ws.s2[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
+          const double xi = ws.xi[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
           const double viol = hinge_b(h, k) - ap;
-          const double r1 = viol - xi + s1, r2 = -xi + s2;
+          const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S), r1 = 0.0, r2 = 0.0;
           const double w1 = l1 * __drcp_rn(s1), w2 = l2 * __drcp_rn(s2), rw = __drcp_rn(w1 + w2), weff = w1 * w2 * rw;
           const double t1 = w1 * r1, t2 = w2 * r2;
           const double rhs_xi = -hw + t1 + t2;
@@ -1051,7 +1055,8 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
       for (int c = 0; c < 4; ++c) { bg[c] = red[8 + c]; rdg[c] = red[12 + c]; }
       Gg[0][0] = red[3]; Gg[0][1] = Gg[1][0] = red[4]; Gg[1][1] = red[5]; Gg[2][2] = red[6]; Gg[3][3] = red[7];
       for (int r = 0; r < 3; ++r) {
-        const double s = gl[12 + r], l = gl[15 + r], rp = gz[r] + s, wgt = l / s;
+        const double s = fmax(-gz[r], TINY_S), l = gl[15 + r], rp = 0.0, wgt = l / s;
+        gl[12 + r] = s;                         // recomputed slack, valid for the rest of this iteration
         comp += s * l; rp_inf = fmax(rp_inf, fabs(rp));
         gl[50 + r] = rp;
         for (int i = 0; i < 4; ++i) {
@@ -1173,10 +1178,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
       double qp = 0.0, qdn = 0.0, qdd = 1.0;
       auto upd_d = [&](double dl, double l) { if (-dl * qdd > qdn * l) { qdn = -dl; qdd = l; } };
       // per-row kernel: returns tau (mode 2) and updates statistics / state
-      auto row = [&](double* ps, double* pl, double gz_h, double gdza, double gdz, double& tau_out) {
-        const double s = *ps, l = *pl;
+      auto row = [&](double* pl, double gz_h, double gdza, double gdz, double& tau_out, double* ps = nullptr) {
+        const double l = *pl;
+        const double s = ps ? *ps : fmax(-gz_h, TINY_S);          // stored slack only for the nonlinear ball row
         const double rs = __drcp_rn(s);
-        const double rp = gz_h + s, wgt = l * rs;
+        const double rp = ps ? gz_h + s : 0.0, wgt = l * rs;
         const double dsa = -rp - gdza, dla = -l - wgt * dsa;
         if (mode == 1) {
           qp = fmax(qp, -dsa * rs); upd_d(dla, l);
@@ -1187,7 +1193,8 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         if (mode == 2) { tau_out = (sigmu - c2 + l * rp) * rs; return; }
         const double ds = -rp - gdz, dl = -l + (sigmu - c2) * rs - wgt * ds;
         if (mode == 3) { qp = fmax(qp, -ds * rs); upd_d(dl, l); return; }
-        *ps = s + al_p * ds; *pl = l + al_d * dl;
+        *pl = l + al_d * dl;
+        if (ps) *ps = s + al_p * ds;
       };
 
       for (int k = tid; k < K; k += nthr) {
@@ -1198,7 +1205,6 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         double bt[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) bt[i] = 0.0;
-        double* st = ST + (size_t)k * STG;
         if (k < K - 1) {
           const double* jac = JAC + (size_t)k * NJ;
           double nu[NX], nua[NX], nud[NX] = {0, 0, 0};
@@ -1213,7 +1219,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int i = 0; i < NX; ++i) { f += sgn(e, i) * nu[i]; fa += sgn(e, i) * nua[i]; fd += sgn(e, i) * nud[i]; }
             double tau = 0.0;
-            row(ws.sP + o, ws.lP + o, f, fa, fd, tau);
+            row(ws.lP + o, f, fa, fd, tau);
             if (mode == 2) {
               stau += tau;
 #pragma unroll
@@ -1239,7 +1245,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int i = 0; i < NX; ++i) { f += sgn(e, i) * dx[i]; fa += sgn(e, i) * da[i]; fd += sgn(e, i) * dz[i]; }
             double tau = 0.0;
-            row(ws.sP + o, ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
+            row(ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
             if (mode == 2) {
               stx += tau;
 #pragma unroll
@@ -1257,7 +1263,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
               f += sgn(e, j) * (w[NX + j] - WR(k, NX + j)); fa += sgn(e, j) * da[NX + j]; fd += sgn(e, j) * dz[NX + j];
             }
             double tau = 0.0;
-            row(ws.sP + o, ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
+            row(ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
             if (mode == 2) {
               stu += tau;
 #pragma unroll
@@ -1271,10 +1277,10 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
           for (int i = 0; i < D; ++i) {
             double tau = 0.0;
             size_t o = (size_t)(Dm::R_P + i) * K + k;
-            row(ws.sP + o, ws.lP + o, w[i] - sc.pos_hi, da[i], (mode >= 3) ? dz[i] : 0.0, tau);
+            row(ws.lP + o, w[i] - sc.pos_hi, da[i], (mode >= 3) ? dz[i] : 0.0, tau);
             if (mode == 2) bt[i] += tau;
             o = (size_t)(Dm::R_P + D + i) * K + k;
-            row(ws.sP + o, ws.lP + o, sc.pos_lo - w[i], -da[i], (mode >= 3) ? -dz[i] : 0.0, tau);
+            row(ws.lP + o, sc.pos_lo - w[i], -da[i], (mode >= 3) ? -dz[i] : 0.0, tau);
             if (mode == 2) bt[i] -= tau;
           }
           if (!BALL) {
@@ -1285,7 +1291,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
               const int c = NX + (r >> 1);
               const double sg = (r & 1) ? -1.0 : 1.0;
               double tau = 0.0;
-              row(ws.sP + o, ws.lP + o, gz[r], sg * da[c], (mode >= 3) ? sg * dz[c] : 0.0, tau);
+              row(ws.lP + o, gz[r], sg * da[c], (mode >= 3) ? sg * dz[c] : 0.0, tau);
               if (mode == 2) bt[c] += sg * tau;
             }
           } else {
@@ -1294,7 +1300,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int j = 0; j < NU; ++j) { n2 += w[NX + j] * w[NX + j]; uda += w[NX + j] * da[NX + j]; udz += w[NX + j] * dz[NX + j]; }
             double tau = 0.0;
-            row(ws.sP + o, ws.lP + o, 0.5 * (n2 - sc.v_max * sc.v_max), uda, (mode >= 3) ? udz : 0.0, tau);
+            row(ws.lP + o, 0.5 * (n2 - sc.v_max * sc.v_max), uda, (mode >= 3) ? udz : 0.0, tau, ws.sB + k);
             if (mode == 2) {
 #pragma unroll
               for (int j = 0; j < NU; ++j) bt[NX + j] += tau * w[NX + j];
@@ -1306,9 +1312,9 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int c = 0; c < D; ++c) { av[c] = hinge_a(h, c, k); ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
             const size_t o = (size_t)h * K + k;
-            const double xi = ws.xi[o], s1 = ws.s1[o], s2 = ws.s2[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
+            const double xi = ws.xi[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
             const double viol = hinge_b(h, k) - ap;
-            const double r1 = viol - xi + s1, r2 = -xi + s2;
+            const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S), r1 = 0.0, r2 = 0.0;
             const double rs1 = __drcp_rn(s1), rs2 = __drcp_rn(s2);
             const double w1 = l1 * rs1, w2 = l2 * rs2, rw = __drcp_rn(w1 + w2);
             // affine step of this hinge pair (sigmu = 0, c = 0)
@@ -1338,7 +1344,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
               qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
               continue;
             }
-            ws.xi[o] = xi + al_p * dxi; ws.s1[o] = s1 + al_p * ds1; ws.s2[o] = s2 + al_p * ds2;
+            ws.xi[o] = xi + al_p * dxi;
             ws.l1[o] = l1 + al_d * dl1; ws.l2[o] = l2 + al_d * dl2;
           }
         }
@@ -1559,7 +1565,7 @@ bool solver_jac_in_smem(int K) {
 template <class M>
 size_t solver_ws_doubles_per_agent(int K, int NH) {
   using Dm = Dims<M>;
-  return (size_t)K * (2 * Dm::NPLAIN + 5 * (size_t)NH);
+  return (size_t)K * (Dm::NPLAIN + 3 * (size_t)NH + (Dm::BALL ? 1 : 0));
 }
 template <class M>
 size_t solver_ws_total_doubles(int n_agents, int K, int NH) {

@@ -278,6 +278,16 @@ class StructIPM:
             upd = lambda v, dv, a, mk: v + a * (dv if mk is None else np.where(np.broadcast_to(mk, dv.shape), dv, 0.0))   # noqa: E731
             sN, sX, sU, sG, sP, sV, s1, s2 = [upd(v, dv, ap, mk) for v, dv, mk in zip(S, dS, masks)]
             lN, lX, lU, lG, lP, lV, l1, l2 = [upd(l, dl_, ad, mk) for l, dl_, mk in zip(L, dL, masks)]
+            # slacks are not independent state in the kernel: every plain row is linear and the start is strictly
+            # feasible, so s = h - G z is RECOMPUTED from the iterate (consistent with z to round-off, half the traffic)
+            tiny = 1e-14
+            gN2, gX2, gU2, gG2, gP2, gV2 = plain_slacks(W, sig, t_nu, t_x, t_u)
+            sN, sX, sU, sG = np.maximum(gN2, tiny), np.maximum(gX2, tiny), np.maximum(gU2, tiny), np.maximum(gG2, tiny)
+            sP = np.where(fm, np.maximum(gP2, tiny), sP)
+            if not self.ball:          # the quadratic ball row keeps its slack as an independent variable
+                sV = np.where(fm, np.maximum(gV2, tiny), sV)
+            viol2 = self.hb - np.einsum("hdk,dk->hk", self.ha, W[:, :d].T)
+            s1 = np.where(hfree, np.maximum(xi - viol2, tiny), s1); s2 = np.where(hfree, np.maximum(xi, tiny), s2)
         X = W[:, :nx].T.copy(); U = W[:, nx:].T.copy()
         return {"X": X, "U": U, "sigma": float(sig), "iters": it, "status": status, "t": (t_nu, t_x, t_u)}
 

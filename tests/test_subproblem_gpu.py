@@ -135,8 +135,8 @@ def test_bad_args_and_workspace(cuda):
     from scvx_b200 import _device, _lib
     lib = _lib.load()
     assert lib.scvx_solve_batched(None, None) == -1
-    assert lib.scvx_solve_workspace_bytes(0, 4, 50, 3, 0) == 4 * 50 * 8 * (2 * 28 + 5 * 3)
-    assert lib.scvx_solve_workspace_bytes(1, 1, 10, 2, 3) == 10 * 8 * (2 * 31 + 5 * 5)
+    assert lib.scvx_solve_workspace_bytes(0, 4, 50, 3, 0) == 4 * 50 * 8 * (28 + 3 * 3)
+    assert lib.scvx_solve_workspace_bytes(1, 1, 10, 2, 3) == 10 * 8 * (31 + 3 * 5 + 1)
     assert lib.scvx_solve_workspace_bytes(9, 1, 10, 0, 0) == 0
     m = omodels.unicycle()
     X, U = m.initialize_trajectory(10)
