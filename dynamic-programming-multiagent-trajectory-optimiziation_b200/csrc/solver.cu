@@ -721,7 +721,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
                         (double)(K - 2) * (2 * D + Dm::NV) + 2.0 * n_active_h * (double)(K - 2);
 
   int status = SCVX_ST_MAXITER, it = 0;
-  const int max_iter = a.max_iter > 0 ? a.max_iter : 60;
+  const int max_iter = a.max_iter > 0 ? a.max_iter : 80;
 
   // =================================================================================================
   // A row pass.  MODE 0: residuals + Newton matrix staging + predictor rhs staging + stationarity staging

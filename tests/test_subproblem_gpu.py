@@ -221,3 +221,17 @@ def test_accuracy_distribution_over_64_scenes(cuda):
     rel = np.array(rel)
     assert np.abs(rel).max() <= OBJ_RTOL, (np.abs(rel).max(), int(np.argmax(np.abs(rel))))
     assert ws.iters.max().item() <= 45
+
+
+def test_long_horizons_K200_and_K220(cuda):
+    """BASELINE config 5 horizon (K=200: factor + Jacobians still fit one block's 227 KB) and K=220, where the FOH
+    Jacobians move to the global workspace (same code path otherwise; 256 threads per agent, strided over stages)."""
+    from scvx_b200 import _lib
+    lib = _lib.load()
+    assert lib.scvx_solve_workspace_bytes(0, 1, 200, 4, 0) == 200 * 8 * (28 + 3 * 4)
+    assert lib.scvx_solve_workspace_bytes(0, 1, 220, 4, 0) == 220 * 8 * (28 + 3 * 4 + 27)     # + K*NJ for the Jacobians
+    rng = np.random.default_rng(5)
+    om = helpers.random_unicycle_scene(rng, 4)
+    for K in (200, 220):
+        pairs = helpers.make_problem_sequence(om, K, 2)
+        check_against_oracle(helpers.solve_batch_on_gpu([p for p, _ in pairs], cuda), pairs)
