@@ -36,6 +36,19 @@ class SolveArgs(ctypes.Structure):
     ]
 
 
+class LtiArgs(ctypes.Structure):
+    """Mirror of `scvx_lti_args` (include/scvx_b200.h)."""
+    _fields_ = [
+        ("n_robots", _c_int), ("T", _c_int), ("n", _c_int), ("m", _c_int), ("nq", _c_int), ("max_iter", _c_int),
+        ("Ad", _c_dp), ("Bd", _c_dp), ("x", _c_dp), ("u", _c_dp), ("x_des", _c_dp),
+        ("tr", _c_dbl), ("c_w", _c_dbl), ("rho", _c_dbl), ("c_S", _c_dbl),
+        ("box_lo0", _c_dbl), ("box_hi0", _c_dbl), ("box_lo1", _c_dbl), ("box_hi1", _c_dbl),
+        ("lin", _c_dp), ("sbar", _c_dp), ("col_h", _c_dp), ("col_g", _c_dp),
+        ("d", _c_dp), ("w", _c_dp), ("S", _c_dp), ("objective", _c_dp), ("status", _c_dp), ("iters", _c_dp),
+        ("workspace", _c_dp), ("workspace_bytes", ctypes.c_ulonglong),
+    ]
+
+
 # name -> (restype, argtypes); must list EVERY symbol include/scvx_b200.h declares
 # (tests/test_capi_symbols.py parses the header and checks).
 SIGNATURES = {
@@ -51,6 +64,9 @@ SIGNATURES = {
     "scvx_solve_batched": (_c_int, [ctypes.POINTER(SolveArgs), _c_dp]),
     "scvx_consensus_update": (_c_int, [_c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),
     "scvx_outer_update": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 11 + [_c_dp]),
+    "scvx_lti_qp_workspace_bytes": (ctypes.c_ulonglong, [_c_int, _c_int, _c_int, _c_int]),
+    "scvx_lti_qp_batched": (_c_int, [ctypes.POINTER(LtiArgs), _c_dp]),
+    "scvx_sbar_qp_batched": (_c_int, [_c_int, _c_int, _c_int, _c_dbl, _c_dbl] + [_c_dp] * 6 + [_c_dp, ctypes.c_ulonglong, _c_dp]),
     "scvx_probe_fp64": (_c_int, [_c_int, _c_int, _c_dp, ctypes.POINTER(_c_dbl), _c_dp]),
     "scvx_l2_flush": (_c_int, [_c_dp, ctypes.c_ulonglong, _c_dp]),
 }

@@ -173,6 +173,44 @@ int scvx_outer_update(int model_id, int n_agents, int K, int M, double conv_tol,
                       int* active, double* metrics, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Distributed_opt scripts -- per-robot perturbation QP of the exact-ZOH double integrator.
+ * Replaces the cvxpy -> CLARABEL solves inside x_traj_opt:
+ *   Distributed_opt/ADMM_decentralized.py:52-98  (n=4, m=2, c_w=100, rho/lin/sbar set, nq=0)
+ *   Distributed_opt/dist_scvx_3d.py:51-111       (n=6, m=3, c_w=1, rho=0, nq = N-1 collision rows, c_S=1e4)
+ *   min c_w sum_{t<T-1} |u_t+w_t|^2 + sum_t [ lin_t.dpos_t + rho/2 |dpos_t - sbar_t|^2 ] + c_S sum_t S_t
+ *   s.t. d_0=0, d_{T-1} = x_des - x_{T-1}, x_{t+1}+d_{t+1} = A(x_t+d_t) + B(u_t+w_t), |w_t|_1 <= tr,
+ *        box on (x_t+d_t)[0:2], h_tq - g_tq.d_t[0:n/2] <= S_t, S_t >= 0          (t = 0..T-2)
+ * Interior-point method with a Riccati recursion per Newton step; one thread block per robot.
+ */
+typedef struct scvx_lti_args {
+  int n_robots, T, n, m;         /* (n, m) = (4, 2) or (6, 3) */
+  int nq;                        /* collision rows per time step (0: none) */
+  int max_iter;                  /* IPM iteration cap (<=0: default 60) */
+  const double *Ad, *Bd;         /* [n*n], [n*m] row-major, shared by all robots (descete_f) */
+  const double *x, *u;           /* [R][T][n], [R][T][m]  current trajectory (row T-1 of u ignored) */
+  const double *x_des;           /* [R][n] */
+  double tr, c_w, rho, c_S;
+  double box_lo0, box_hi0, box_lo1, box_hi1;
+  const double *lin, *sbar;      /* [R][T][2] or NULL */
+  const double *col_h, *col_g;   /* [R][nq][T-1], [R][nq][n/2][T-1] or NULL */
+  double *d, *w;                 /* out: [R][T][n], [R][T][m] (row T-1 of w is 0) */
+  double *S;                     /* out: [R][T] collision slack (hinge value), may be NULL */
+  double *objective;             /* out: [R] */
+  int *status, *iters;           /* out: [R] */
+  void* workspace; unsigned long long workspace_bytes;
+} scvx_lti_args;
+unsigned long long scvx_lti_qp_workspace_bytes(int n_robots, int T, int n, int nq);
+int scvx_lti_qp_batched(const scvx_lti_args* args, void* stream);
+
+/* Per-(robot, t) consensus QP of ADMM_decentralized.py:106-139 (separable over t):
+ *   min_{sbar_t in R^2, S_t >= 0} r_t.(s_t - sbar_t) + rho/2 |s_t - sbar_t|^2 + c_S S_t   s.t. h_tq - g_tq.sbar_t <= S_t.
+ * s_pos, r_dual, sbar: [R][T][2]; col_h [R][nq][T]; col_g [R][nq][2][T]; S_out [R][T] or NULL;
+ * workspace: n_robots*T*2*nq doubles. */
+int scvx_sbar_qp_batched(int n_robots, int T, int nq, double rho, double c_S, const double* s_pos, const double* r_dual,
+                         const double* col_h, const double* col_g, double* sbar, double* S_out,
+                         void* workspace, unsigned long long workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py only; not on the product path).
  * scvx_probe_fp64: `blocks` x 256 threads x `iters` x 8 independent DFMA; *flops_h (HOST pointer) receives the flop
  * count of the launch; `out` needs blocks*256 doubles.  scvx_l2_flush: write sweep over a buffer (> L2) between timed steps.
