@@ -40,11 +40,12 @@ def test_library_exports_every_declared_symbol():
     assert lib.scvx_model_dims(99, None, None, None) == -1
 
 
-def test_solve_args_struct_matches_header():
-    """Field order of the ctypes mirror == field order of `scvx_solve_args` in the header."""
+@pytest.mark.parametrize("cname,pyname", [("scvx_solve_args", "SolveArgs"), ("scvx_lti_args", "LtiArgs")])
+def test_args_structs_match_header(cname, pyname):
+    """Field order of the ctypes mirrors == field order of the structs in the header."""
     from scvx_b200 import _lib
     src = open(os.path.join(ROOT, "include", "scvx_b200.h")).read()
-    body = re.search(r"typedef struct scvx_solve_args \{(.*?)\} scvx_solve_args;", src, flags=re.S).group(1)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     fields = []
     for stmt in body.split(";"):
@@ -53,4 +54,4 @@ def test_solve_args_struct_matches_header():
             continue
         stmt = re.sub(r"^(const\s+)?(unsigned\s+long\s+long|unsigned\s+char|double|int|void)\s*", "", stmt)
         fields += [f.strip().lstrip("*").strip() for f in stmt.split(",")]
-    assert fields == [f[0] for f in _lib.SolveArgs._fields_]
+    assert fields == [f[0] for f in getattr(_lib, pyname)._fields_]
