@@ -30,7 +30,7 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared object next to this file."""
     if not force and not needs_build():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("SCVX_NVCC_EXTRA", "").split()
     objs = []
     procs = []
     for s in SOURCES:

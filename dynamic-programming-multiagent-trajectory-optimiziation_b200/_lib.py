@@ -69,6 +69,7 @@ SIGNATURES = {
     "scvx_sbar_qp_batched": (_c_int, [_c_int, _c_int, _c_int, _c_dbl, _c_dbl] + [_c_dp] * 6 + [_c_dp, ctypes.c_ulonglong, _c_dp]),
     "scvx_probe_fp64": (_c_int, [_c_int, _c_int, _c_dp, ctypes.POINTER(_c_dbl), _c_dp]),
     "scvx_l2_flush": (_c_int, [_c_dp, ctypes.c_ulonglong, _c_dp]),
+    "scvx_debug_phase_cycles": (_c_int, [ctypes.POINTER(ctypes.c_ulonglong), _c_int]),
 }
 
 _lib = None

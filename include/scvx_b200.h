@@ -217,6 +217,9 @@ int scvx_sbar_qp_batched(int n_robots, int T, int nq, double rho, double c_S, co
  */
 int scvx_probe_fp64(int blocks, int iters, double* out, double* flops_h, void* stream);
 int scvx_l2_flush(double* buf, unsigned long long n_doubles, void* stream);
+/* scvx_debug_phase_cycles: SM cycles block 0 of scvx_solve_batched spent in each kernel phase (out32: 32 counters on the HOST;
+ * all zero unless the library was built with -DSCVX_PHASE_TIMING, see tools/phase_timing.py). */
+int scvx_debug_phase_cycles(unsigned long long* out32, int reset);
 
 #ifdef __cplusplus
 }
