@@ -85,6 +85,15 @@ __device__ __forceinline__ double rsqrt_fast(double a) {
   return fma(x, e, x);
 }
 
+// One hinge row pair of one stage, fetched one hinge ahead of its use: the row state comes from L2 (the L1 left beside
+// 2 x 113 KB of shared memory cannot hold it) and the hinge loop has a run-time trip count, so without the software
+// pipeline every hinge pays a full round trip.
+template <int D>
+struct HingeData {
+  double a[D], b, xi, l1, l2;
+  bool on;
+};
+
 struct AgentPtrs {
   double *lP;                          // [NPLAIN][K]  multipliers of the plain rows
   double *sB;                          // [K]          stored slack of the (nonlinear) ball row, single integrator only
@@ -253,30 +262,63 @@ __device__ __forceinline__ void cr_factor(double* A, double* B, double* C, int n
   for (int s = 1; s <= n; s <<= 1) {
     const int cnt = (n / s + 1) >> 1;            // odd nodes j = s (2m+1) <= n
     const int npr = nthr / NS;                   // nodes per round: the NS columns of a node always share a round
-    // ---- phase 1: pivot inverse, P, Q, push-left update of D_{j-s}
+    // One compute section per round: thread (j, c) derives from shared memory -- untouched until the barrier -- the
+    // pivot's inverse factor, column c of P_j and Q_j, the push-left update of D_{j-s} and the push-right update of
+    // D_{j+s} with the new left coupling of node j+s.  The stores follow in two sections: the two pushes into an even
+    // node come from different threads and must not interleave.
     for (int base = 0; base < cnt; base += npr) {
       const int m = base + tid / NS;
       const bool on = (tid < npr * NS) && (m < cnt);
       int j = 0, c = 0, a = 0, b = 0;
-      double Dl[NS][NS], Lj[NS][NS];
+      double Li[NS][NS], pc[NS], qc[NS], upd[NS], a1[NS], a2[NS];
       if (on) {
         c = tid - (tid / NS) * NS;
         j = s * (2 * m + 1); a = j - s; b = j + s;
         const double* dj = A + (size_t)j * SD;
-#pragma unroll
-        for (int i = 0; i < NS; ++i)
-#pragma unroll
-          for (int q = 0; q <= i; ++q) Dl[i][q] = dj[i * NS + q];
         const double* lj = B + (size_t)j * SD;
+        {
+          double Dl[NS][NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i)
+          for (int i = 0; i < NS; ++i)
 #pragma unroll
-          for (int q = 0; q < NS; ++q) Lj[i][q] = (a >= 1) ? lj[i * NS + q] : 0.0;
+            for (int q = 0; q <= i; ++q) Dl[i][q] = dj[i * NS + q];
+          chol_inverse<NS>(Dl, Li);
+        }
+        double x[NS];
+        if (a >= 1) {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) x[i] = lj[i * NS + c];
+          apply_dinv<NS>(Li, x, pc);
+#pragma unroll
+          for (int r = 0; r < NS; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acc += lj[i * NS + r] * pc[i];
+            upd[r] = acc;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) { pc[i] = 0.0; upd[i] = 0.0; }
+        }
+        if (b <= n) {
+          const double* lb = B + (size_t)b * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) x[i] = lb[c * NS + i];      // column c of H[j, b] = row c of H[b, j]
+          apply_dinv<NS>(Li, x, qc);
+#pragma unroll
+          for (int r = 0; r < NS; ++r) {
+            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { const double l = lb[r * NS + i]; s1 += l * qc[i]; s2 += l * pc[i]; }
+            a1[r] = s1; a2[r] = s2;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < NS; ++i) { qc[i] = 0.0; a1[i] = 0.0; a2[i] = 0.0; }
+        }
       }
       __syncthreads();
       if (on) {
-        double Li[NS][NS];
-        chol_inverse<NS>(Dl, Li);
         if (c == 0) {
           double* dj = A + (size_t)j * SD;
 #pragma unroll
@@ -284,73 +326,26 @@ __device__ __forceinline__ void cr_factor(double* A, double* B, double* C, int n
 #pragma unroll
             for (int q = 0; q < NS; ++q) dj[i * NS + q] = (q <= i) ? Li[i][q] : 0.0;
         }
-        double x[NS], pc[NS], qc[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) x[i] = Lj[i][c];
-        apply_dinv<NS>(Li, x, pc);
         double* pj = B + (size_t)j * SD;
+        double* qj = C + (size_t)j * SD;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) pj[i * NS + c] = pc[i];
+        for (int i = 0; i < NS; ++i) { pj[i * NS + c] = pc[i]; qj[i * NS + c] = qc[i]; }
         if (a >= 1) {
           double* da = A + (size_t)a * SD;
 #pragma unroll
-          for (int r = 0; r < NS; ++r) {
-            double acc = 0.0;
-#pragma unroll
-            for (int i = 0; i < NS; ++i) acc += Lj[i][r] * pc[i];
-            da[r * NS + c] -= acc;
-          }
+          for (int r = 0; r < NS; ++r) da[r * NS + c] -= upd[r];
         }
         if (b <= n) {
-          const double* lb = B + (size_t)b * SD;
+          double* lb = B + (size_t)b * SD;
 #pragma unroll
-          for (int i = 0; i < NS; ++i) x[i] = lb[c * NS + i];      // column c of H[j, b] = row c of H[b, j]
-          apply_dinv<NS>(Li, x, qc);
-        } else {
-#pragma unroll
-          for (int i = 0; i < NS; ++i) qc[i] = 0.0;
-        }
-        double* qj = C + (size_t)j * SD;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) qj[i * NS + c] = qc[i];
-      }
-      __syncthreads();
-    }
-    // ---- phase 2: push-right update of D_{j+s} and the new left coupling of node j+s
-    for (int base = 0; base < cnt; base += npr) {
-      const int m = base + tid / NS;
-      int j = 0, c = 0, b = 0;
-      bool on = (tid < npr * NS) && (m < cnt);
-      double Lb[NS][NS];
-      if (on) {
-        c = tid - (tid / NS) * NS;
-        j = s * (2 * m + 1); b = j + s;
-        on = (b <= n);
-        if (on) {
-          const double* lb = B + (size_t)b * SD;
-#pragma unroll
-          for (int i = 0; i < NS; ++i)
-#pragma unroll
-            for (int q = 0; q < NS; ++q) Lb[i][q] = lb[i * NS + q];
+          for (int r = 0; r < NS; ++r) lb[r * NS + c] = -a2[r];
         }
       }
       __syncthreads();
-      if (on) {
-        const double* pj = B + (size_t)j * SD;
-        const double* qj = C + (size_t)j * SD;
+      if (on && b <= n) {
         double* db = A + (size_t)b * SD;
-        double* lb = B + (size_t)b * SD;
-        double pc[NS], qc[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { pc[i] = pj[i * NS + c]; qc[i] = qj[i * NS + c]; }
-#pragma unroll
-        for (int r = 0; r < NS; ++r) {
-          double a1 = 0.0, a2 = 0.0;
-#pragma unroll
-          for (int i = 0; i < NS; ++i) { a1 += Lb[r][i] * qc[i]; a2 += Lb[r][i] * pc[i]; }
-          db[r * NS + c] -= a1;
-          lb[r * NS + c] = -a2;
-        }
+        for (int r = 0; r < NS; ++r) db[r * NS + c] -= a1[r];
       }
       __syncthreads();
     }
@@ -363,96 +358,149 @@ __device__ __forceinline__ double* rhs_col(double* Rb, double* dW, int k, int c)
   return (NC == 1 || c == 4) ? (dW + (size_t)k * Dm::NSP) : (Rb + (size_t)k * Dm::SR + c * Dm::NS);
 }
 
+// NC == 5: work items are (node, column); NC == 1 (the corrector's single right-hand side): items are (node, ROW), so
+// that the five rows of a node's update run on five threads instead of in one dependent chain.
 template <class Dm, int NC>
 __device__ __forceinline__ void cr_forward(const double* B, const double* C, double* Rb, double* dW, int n, int tid, int nthr) {
   constexpr int NS = Dm::NS, SD = Dm::SD;
   for (int s = 1; 2 * s <= n; s <<= 1) {
-    const int items = (n / (2 * s)) * NC;          // even nodes a = 2 s (m+1)
-    for (int it = tid; it < items; it += nthr) {
-      const int m = it / NC, c = (NC == 1) ? 4 : it - m * NC;
-      const int a = 2 * s * (m + 1), jl = a - s, jr = a + s;
-      double* va = rhs_col<Dm, NC>(Rb, dW, a, c);
-      const double* vl = rhs_col<Dm, NC>(Rb, dW, jl, c);
-      const double* ql = C + (size_t)jl * SD;
-      double v[NS];
-#pragma unroll
-      for (int r = 0; r < NS; ++r) {
-        double acc = va[r];
+    const int nodes = n / (2 * s);                 // even nodes a = 2 s (m+1)
+    if (NC == 1) {
+      for (int it = tid; it < nodes * NS; it += nthr) {
+        const int m = it / NS, r = it - m * NS;
+        const int a = 2 * s * (m + 1), jl = a - s, jr = a + s;
+        double* va = dW + (size_t)a * Dm::NSP;
+        const double* vl = dW + (size_t)jl * Dm::NSP;
+        const double* ql = C + (size_t)jl * SD;
+        double acc = va[r], acc2 = 0.0;
 #pragma unroll
         for (int i = 0; i < NS; ++i) acc -= ql[i * NS + r] * vl[i];
-        v[r] = acc;
+        if (jr <= n) {
+          const double* vr = dW + (size_t)jr * Dm::NSP;
+          const double* pr = B + (size_t)jr * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) acc2 += pr[i * NS + r] * vr[i];
+        }
+        va[r] = acc - acc2;
       }
-      if (jr <= n) {
-        const double* vr = rhs_col<Dm, NC>(Rb, dW, jr, c);
-        const double* pr = B + (size_t)jr * SD;
+    } else {
+      for (int it = tid; it < nodes * NC; it += nthr) {
+        const int m = it / NC, c = it - m * NC;
+        const int a = 2 * s * (m + 1), jl = a - s, jr = a + s;
+        double* va = rhs_col<Dm, NC>(Rb, dW, a, c);
+        const double* vl = rhs_col<Dm, NC>(Rb, dW, jl, c);
+        const double* ql = C + (size_t)jl * SD;
+        double v[NS];
 #pragma unroll
         for (int r = 0; r < NS; ++r) {
-          double acc = 0.0;
+          double acc = va[r];
 #pragma unroll
-          for (int i = 0; i < NS; ++i) acc += pr[i * NS + r] * vr[i];
-          v[r] -= acc;
+          for (int i = 0; i < NS; ++i) acc -= ql[i * NS + r] * vl[i];
+          v[r] = acc;
         }
-      }
+        if (jr <= n) {
+          const double* vr = rhs_col<Dm, NC>(Rb, dW, jr, c);
+          const double* pr = B + (size_t)jr * SD;
 #pragma unroll
-      for (int r = 0; r < NS; ++r) va[r] = v[r];
+          for (int r = 0; r < NS; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) acc += pr[i * NS + r] * vr[i];
+            v[r] -= acc;
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < NS; ++r) va[r] = v[r];
+      }
     }
     __syncthreads();
   }
   if (n < 2) __syncthreads();
 }
 
+// u_j = D_j^-1 v_j = Li_j' (Li_j v_j) for every node at once (the forward-eliminated right-hand sides are final), so
+// that the backward sweep is a plain x_j = u_j - P_j x_{j-s} - Q_j x_{j+s} without the dependent triangular products.
+template <class Dm>
+__device__ __forceinline__ void cr_apply_dinv_all(const double* A, double* dW, int n, int tid, int nthr) {
+  constexpr int NS = Dm::NS, SD = Dm::SD;
+  for (int j = 1 + tid; j <= n; j += nthr) {
+    double Li[NS][NS], x[NS], y[NS];
+    const double* li = A + (size_t)j * SD;
+    double* v = dW + (size_t)j * Dm::NSP;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+      x[i] = v[i];
+#pragma unroll
+      for (int q = 0; q < NS; ++q) Li[i][q] = (q <= i) ? li[i * NS + q] : 0.0;
+    }
+    apply_dinv<NS>(Li, x, y);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) v[i] = y[i];
+  }
+  __syncthreads();
+}
+
+// Backward sweep on right-hand sides already multiplied by D^-1 (cr_apply_dinv_all / the Schur-complement pass).
 template <class Dm, int NC>
-__device__ __forceinline__ void cr_backward(const double* A, const double* B, const double* C, double* Rb, double* dW, int n,
-                                            int tid, int nthr) {
+__device__ __forceinline__ void cr_backward(const double* B, const double* C, double* Rb, double* dW, int n, int tid, int nthr) {
   constexpr int NS = Dm::NS, SD = Dm::SD;
   int s = 1;
   while (2 * s <= n) s <<= 1;
   for (; s >= 1; s >>= 1) {
-    const int items = ((n / s + 1) >> 1) * NC;     // odd nodes j = s (2m+1)
-    for (int it = tid; it < items; it += nthr) {
-      const int m = it / NC, c = (NC == 1) ? 4 : it - m * NC;
-      const int j = s * (2 * m + 1), jl = j - s, jr = j + s;
-      double* vj = rhs_col<Dm, NC>(Rb, dW, j, c);
-      const double* li = A + (size_t)j * SD;
-      double t[NS], x[NS];
+    const int nodes = (n / s + 1) >> 1;            // odd nodes j = s (2m+1)
+    if (NC == 1) {
+      for (int it = tid; it < nodes * NS; it += nthr) {
+        const int m = it / NS, i = it - m * NS;
+        const int j = s * (2 * m + 1), jl = j - s, jr = j + s;
+        double* vj = dW + (size_t)j * Dm::NSP;
+        double acc = vj[i], acc2 = 0.0;
+        if (jl >= 1) {
+          const double* vl = dW + (size_t)jl * Dm::NSP;
+          const double* pj = B + (size_t)j * SD + i * NS;
 #pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int q = 0; q <= i; ++q) acc += li[i * NS + q] * vj[q];
-        t[i] = acc;
-      }
-#pragma unroll
-      for (int i = 0; i < NS; ++i) {
-        double acc = 0.0;
-#pragma unroll
-        for (int q = i; q < NS; ++q) acc += li[q * NS + i] * t[q];
-        x[i] = acc;
-      }
-      if (jl >= 1) {
-        const double* vl = rhs_col<Dm, NC>(Rb, dW, jl, c);
-        const double* pj = B + (size_t)j * SD;
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int q = 0; q < NS; ++q) acc += pj[i * NS + q] * vl[q];
-          x[i] -= acc;
+          for (int q = 0; q < NS; ++q) acc -= pj[q] * vl[q];
         }
-      }
-      if (jr <= n) {
-        const double* vr = rhs_col<Dm, NC>(Rb, dW, jr, c);
-        const double* qj = C + (size_t)j * SD;
+        if (jr <= n) {
+          const double* vr = dW + (size_t)jr * Dm::NSP;
+          const double* qj = C + (size_t)j * SD + i * NS;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) {
-          double acc = 0.0;
-#pragma unroll
-          for (int q = 0; q < NS; ++q) acc += qj[i * NS + q] * vr[q];
-          x[i] -= acc;
+          for (int q = 0; q < NS; ++q) acc2 += qj[q] * vr[q];
         }
+        vj[i] = acc - acc2;
       }
+    } else {
+      for (int it = tid; it < nodes * NC; it += nthr) {
+        const int m = it / NC, c = it - m * NC;
+        const int j = s * (2 * m + 1), jl = j - s, jr = j + s;
+        double* vj = rhs_col<Dm, NC>(Rb, dW, j, c);
+        double x[NS];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) vj[i] = x[i];
+        for (int i = 0; i < NS; ++i) x[i] = vj[i];
+        if (jl >= 1) {
+          const double* vl = rhs_col<Dm, NC>(Rb, dW, jl, c);
+          const double* pj = B + (size_t)j * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) acc += pj[i * NS + q] * vl[q];
+            x[i] -= acc;
+          }
+        }
+        if (jr <= n) {
+          const double* vr = rhs_col<Dm, NC>(Rb, dW, jr, c);
+          const double* qj = C + (size_t)j * SD;
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) acc += qj[i * NS + q] * vr[q];
+            x[i] -= acc;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) vj[i] = x[i];
+      }
     }
     __syncthreads();
   }
@@ -573,6 +621,21 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
   };
   auto hinge_on = [&](int h) -> bool { return (h < Mobs) || !col_mask || col_mask[h - Mobs]; };
   auto hinge_w = [&](int h) -> double { return (h < Mobs) ? sc.hw_obs : sc.hw_col; };
+  auto load_hinge = [&](int h, int k) -> HingeData<D> {
+    HingeData<D> r;
+    r.on = (h < NH) && hinge_on(h);
+    r.b = 0.0; r.xi = 1.0; r.l1 = 1.0; r.l2 = 1.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) r.a[c] = 0.0;
+    if (r.on) {
+      const size_t o = (size_t)h * K + k;
+#pragma unroll
+      for (int c = 0; c < D; ++c) r.a[c] = hinge_a(h, c, k);
+      r.b = hinge_b(h, k);
+      r.xi = ws.xi[o]; r.l1 = ws.l1[o]; r.l2 = ws.l2[o];
+    }
+    return r;
+  };
 
   // ---- load problem data into shared memory ---------------------------------------------------------
   const double* Xr = a.X_ref + (size_t)agent * NX * K;
@@ -907,14 +970,16 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
           }
         }
         // hinge rows
+        HingeData<D> hnx = load_hinge(0, k);
         for (int h = 0; h < NH; ++h) {
-          if (!hinge_on(h)) continue;
+          const HingeData<D> hd = hnx;
+          hnx = load_hinge(h + 1, k);
+          if (!hd.on) continue;
           double av[D], ap = 0.0;
 #pragma unroll
-          for (int c = 0; c < D; ++c) { av[c] = hinge_a(h, c, k); ap += av[c] * w[c]; }
-          const size_t o = (size_t)h * K + k;
-          const double xi = ws.xi[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
-          const double viol = hinge_b(h, k) - ap;
+          for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; }
+          const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
+          const double viol = hd.b - ap;
           const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S), r1 = 0.0, r2 = 0.0;
           const double w1 = l1 * rcp_fast(s1), w2 = l2 * rcp_fast(s2), rw = rcp_fast(w1 + w2), weff = w1 * w2 * rw;
           const double t1 = w1 * r1, t2 = w2 * r2;
@@ -1147,13 +1212,21 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         double Z[5][NS];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          const double* v = (c < 4) ? (Rb + (size_t)k * SR + c * NS) : (dW + k * NSP);
+          double* v = (c < 4) ? (Rb + (size_t)k * SR + c * NS) : (dW + k * NSP);
 #pragma unroll
           for (int i = 0; i < NS; ++i) {
             double acc = 0.0;
 #pragma unroll
             for (int j = 0; j <= i; ++j) acc += li[i * NS + j] * v[j];
             Z[c][i] = acc;
+          }
+          // the backward sweep wants D^-1 v = Li' (Li v): finish it here, in place, while Li and Z are at hand
+#pragma unroll
+          for (int i = 0; i < NS; ++i) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = i; j < NS; ++j) acc += li[j * NS + i] * Z[c][j];
+            v[i] = acc;
           }
         }
         int q = 0;
@@ -1185,7 +1258,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
       __syncthreads();
     }
     PHASE(5);
-    cr_backward<Dm, 5>(Dk, Ek, Ck, Rb, dW, K - 2, tid, nthr);
+    cr_backward<Dm, 5>(Ek, Ck, Rb, dW, K - 2, tid, nthr);
     PHASE(6);
     // dWa = v - Y dg_aff
     {
@@ -1221,8 +1294,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
       double qp = 0.0, qdn = 0.0, qdd = 1.0;
       auto upd_d = [&](double dl, double l) { if (-dl * qdd > qdn * l) { qdn = -dl; qdd = l; } };
       // per-row kernel: returns tau (mode 2) and updates statistics / state
-      auto row = [&](double* pl, double gz_h, double gdza, double gdz, double& tau_out, double* ps = nullptr) {
-        const double l = *pl;
+      auto row = [&](double* pl, double l, double gz_h, double gdza, double gdz, double& tau_out, double* ps = nullptr) {
         const double s = ps ? *ps : fmax(-gz_h, TINY_S);          // stored slack only for the nonlinear ball row
         const double rs = rcp_fast(s);
         const double rp = ps ? gz_h + s : 0.0, wgt = l * rs;
@@ -1245,6 +1317,16 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         const double* da = dWa + k * NSP;
         const double* dz = dW + k * NSP;       // valid in modes 3, 4 (final direction)
         const bool fr = (k > 0 && k < K - 1);
+        // mode 4 stores into the row state, so the compiler cannot hoist later loads above earlier stores: fetch the
+        // stage's plain-row multipliers in one batch first.  (Modes 1-3 are store-free and schedule their loads freely.)
+        double lp4[mode == 4 ? NPLAIN : 1];
+        if (mode == 4) {
+#pragma unroll
+          for (int r = 0; r < Dm::R_P; ++r) lp4[mode == 4 ? r : 0] = (r >= NEX || k < K - 1) ? ws.lP[(size_t)r * K + k] : 0.0;
+#pragma unroll
+          for (int r = Dm::R_P; r < NPLAIN; ++r) lp4[mode == 4 ? r : 0] = fr ? ws.lP[(size_t)r * K + k] : 0.0;
+        }
+        auto LP = [&](int r, size_t o) -> double { return (mode == 4) ? lp4[mode == 4 ? r : 0] : ws.lP[o]; };
         double bt[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) bt[i] = 0.0;
@@ -1262,7 +1344,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int i = 0; i < NX; ++i) { f += sgn(e, i) * nu[i]; fa += sgn(e, i) * nua[i]; fd += sgn(e, i) * nud[i]; }
             double tau = 0.0;
-            row(ws.lP + o, f, fa, fd, tau);
+            row(ws.lP + o, LP(Dm::R_NU + e, o), f, fa, fd, tau);
             if (mode == 2) {
               stau += tau;
 #pragma unroll
@@ -1288,7 +1370,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int i = 0; i < NX; ++i) { f += sgn(e, i) * dx[i]; fa += sgn(e, i) * da[i]; fd += sgn(e, i) * dz[i]; }
             double tau = 0.0;
-            row(ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
+            row(ws.lP + o, LP(Dm::R_X + e, o), f, fa, (mode >= 3) ? fd : 0.0, tau);
             if (mode == 2) {
               stx += tau;
 #pragma unroll
@@ -1306,7 +1388,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
               f += sgn(e, j) * (w[NX + j] - WR(k, NX + j)); fa += sgn(e, j) * da[NX + j]; fd += sgn(e, j) * dz[NX + j];
             }
             double tau = 0.0;
-            row(ws.lP + o, f, fa, (mode >= 3) ? fd : 0.0, tau);
+            row(ws.lP + o, LP(Dm::R_U + e, o), f, fa, (mode >= 3) ? fd : 0.0, tau);
             if (mode == 2) {
               stu += tau;
 #pragma unroll
@@ -1320,10 +1402,10 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
           for (int i = 0; i < D; ++i) {
             double tau = 0.0;
             size_t o = (size_t)(Dm::R_P + i) * K + k;
-            row(ws.lP + o, w[i] - sc.pos_hi, da[i], (mode >= 3) ? dz[i] : 0.0, tau);
+            row(ws.lP + o, LP(Dm::R_P + i, o), w[i] - sc.pos_hi, da[i], (mode >= 3) ? dz[i] : 0.0, tau);
             if (mode == 2) bt[i] += tau;
             o = (size_t)(Dm::R_P + D + i) * K + k;
-            row(ws.lP + o, sc.pos_lo - w[i], -da[i], (mode >= 3) ? -dz[i] : 0.0, tau);
+            row(ws.lP + o, LP(Dm::R_P + D + i, o), sc.pos_lo - w[i], -da[i], (mode >= 3) ? -dz[i] : 0.0, tau);
             if (mode == 2) bt[i] -= tau;
           }
           if (!BALL) {
@@ -1334,7 +1416,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
               const int c = NX + (r >> 1);
               const double sg = (r & 1) ? -1.0 : 1.0;
               double tau = 0.0;
-              row(ws.lP + o, gz[r], sg * da[c], (mode >= 3) ? sg * dz[c] : 0.0, tau);
+              row(ws.lP + o, LP(Dm::R_V + r, o), gz[r], sg * da[c], (mode >= 3) ? sg * dz[c] : 0.0, tau);
               if (mode == 2) bt[c] += sg * tau;
             }
           } else {
@@ -1343,20 +1425,23 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
 #pragma unroll
             for (int j = 0; j < NU; ++j) { n2 += w[NX + j] * w[NX + j]; uda += w[NX + j] * da[NX + j]; udz += w[NX + j] * dz[NX + j]; }
             double tau = 0.0;
-            row(ws.lP + o, 0.5 * (n2 - sc.v_max * sc.v_max), uda, (mode >= 3) ? udz : 0.0, tau, ws.sB + k);
+            row(ws.lP + o, LP(Dm::R_V, o), 0.5 * (n2 - sc.v_max * sc.v_max), uda, (mode >= 3) ? udz : 0.0, tau, ws.sB + k);
             if (mode == 2) {
 #pragma unroll
               for (int j = 0; j < NU; ++j) bt[NX + j] += tau * w[NX + j];
             }
           }
+          HingeData<D> hnx = load_hinge(0, k);
           for (int h = 0; h < NH; ++h) {
-            if (!hinge_on(h)) continue;
+            const HingeData<D> hd = hnx;
+            hnx = load_hinge(h + 1, k);
+            if (!hd.on) continue;
             double av[D], ap = 0.0, ada = 0.0, adz = 0.0;
 #pragma unroll
-            for (int c = 0; c < D; ++c) { av[c] = hinge_a(h, c, k); ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
+            for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
             const size_t o = (size_t)h * K + k;
-            const double xi = ws.xi[o], l1 = ws.l1[o], l2 = ws.l2[o], hw = hinge_w(h);
-            const double viol = hinge_b(h, k) - ap;
+            const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
+            const double viol = hd.b - ap;
             const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S), r1 = 0.0, r2 = 0.0;
             const double rs1 = rcp_fast(s1), rs2 = rcp_fast(s2);
             const double w1 = l1 * rs1, w2 = l2 * rs2, rw = rcp_fast(w1 + w2);
@@ -1490,7 +1575,8 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         PHASE(18);
         cr_forward<Dm, 1>(Ek, Ck, Rb, dW, K - 2, tid, nthr);
         PHASE(16);
-        cr_backward<Dm, 1>(Dk, Ek, Ck, Rb, dW, K - 2, tid, nthr);
+        cr_apply_dinv_all<Dm>(Dk, dW, K - 2, tid, nthr);
+        cr_backward<Dm, 1>(Ek, Ck, Rb, dW, K - 2, tid, nthr);
         PHASE(17);
         {
           const double g0 = gl[8], g1 = gl[9], g2 = gl[10], g3 = gl[11];
