@@ -168,3 +168,55 @@ def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_
     a.workspace, a.workspace_bytes = ptr(ws.scratch), ws.nbytes
     check(load().scvx_solve_batched(ctypes.byref(a), stream_ptr()), "scvx_solve_batched")
     return ws
+
+
+def warm_start(model_id, p0, p1, obs_c, obs_r, clearance, K, obs_count=None):
+    """Batched initial_guess (SCvx/utils/initial_guess.py:61-107, IS_initial_guess.py:87-126).
+
+    p0, p1 (n, 3); obs_c (n, M_max, d); obs_r (n, M_max); obs_count (n,) int32 or None -> X0 (n, 3, K), U0 (n, n_u, K),
+    status (n,) int32 (see include/scvx_b200.h)."""
+    _, n_u, d = MODEL_DIMS[model_id]
+    p0, p1 = _dev(p0), _dev(p1)
+    n = p0.shape[0]
+    assert p0.shape == (n, 3) and p1.shape == (n, 3)
+    M = 0 if obs_c is None else obs_c.shape[1]
+    if M:
+        obs_c, obs_r = _dev(obs_c), _dev(obs_r)
+        assert obs_c.shape == (n, M, d) and obs_r.shape == (n, M)
+    if obs_count is not None:
+        assert obs_count.is_cuda and obs_count.dtype == torch.int32 and obs_count.shape == (n,)
+        obs_count = obs_count.contiguous()
+    X0 = torch.empty((n, 3, K), dtype=F64, device=p0.device)
+    U0 = torch.empty((n, n_u, K), dtype=F64, device=p0.device)
+    status = torch.empty((n,), dtype=torch.int32, device=p0.device)
+    check(load().scvx_warm_start_batched(model_id, n, K, M, ptr(p0), ptr(p1), ptr(obs_c) if M else None,
+                                         ptr(obs_r) if M else None, ptr(obs_count), float(clearance), ptr(X0), ptr(U0),
+                                         ptr(status), stream_ptr()), "scvx_warm_start_batched")
+    return X0, U0, status
+
+
+def min_inter_agent_distance(X, n_rows=3):
+    """analysis.py:10-31 on a stacked (N, n_x, K) tensor -> (d_min (1,), d_mat (N, N))."""
+    X = _dev(X)
+    N, n_x, K = X.shape
+    d_mat = torch.empty((N, N), dtype=F64, device=X.device)
+    d_min = torch.empty((1,), dtype=F64, device=X.device)
+    check(load().scvx_min_inter_agent_distance(N, K, n_x, n_rows, ptr(X), ptr(d_mat), ptr(d_min), stream_ptr()),
+          "scvx_min_inter_agent_distance")
+    return d_min, d_mat
+
+
+def min_agent_obstacle_distance(X, obs_c, obs_r, robot_radius, n_rows=3):
+    """analysis.py:34-62 on a stacked (N, n_x, K) tensor; obs_c (M, n_rows), obs_r (M,) -> (d_min (1,), d_mat (N, M))."""
+    X = _dev(X)
+    N, n_x, K = X.shape
+    M = obs_c.shape[0]
+    d_mat = torch.full((N, M), float("inf"), dtype=F64, device=X.device)
+    d_min = torch.empty((1,), dtype=F64, device=X.device)
+    if M:
+        obs_c, obs_r = _dev(obs_c), _dev(obs_r)
+        assert obs_c.shape == (M, n_rows) and obs_r.shape == (M,)
+    check(load().scvx_min_agent_obstacle_distance(N, K, n_x, n_rows, M, ptr(X), ptr(obs_c) if M else None,
+                                                  ptr(obs_r) if M else None, float(robot_radius), ptr(d_mat), ptr(d_min),
+                                                  stream_ptr()), "scvx_min_agent_obstacle_distance")
+    return d_min, d_mat

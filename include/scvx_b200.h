@@ -211,6 +211,35 @@ int scvx_sbar_qp_batched(int n_robots, int T, int nq, double rho, double c_S, co
                          void* workspace, unsigned long long workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Callers either side of the loop (SURVEY section 8 f, ranks 2 and 4).
+ *
+ * scvx_warm_start_batched -- replaces initial_guess() of SCvx/utils/initial_guess.py:61-107 (model UNICYCLE: tangent
+ * way-points around inflated discs, headings from forward differences, U0 = 0) and of SCvx/utils/IS_initial_guess.py:87-126
+ * (model SINGLE_INTEGRATOR: detour way-points around inflated spheres, U0 = forward differences / dt, dt = 1/(K-1)).
+ *   p0, p1 [n_agents][3] (unicycle: x, y, theta -- theta is ignored, as in the reference); obs_c [n_agents][M_max][d];
+ *   obs_r [n_agents][M_max] (NOT inflated; `clearance` is added here); obs_count [n_agents] or NULL (= M_max each);
+ *   X0 [n_agents][3][K]; U0 [n_agents][n_u][K].
+ *   status [n_agents]: 0 ok; 1 start/goal inside or on an inflated obstacle that the straight segment crosses (the reference
+ *   raises ValueError "Point inside/on circle"); 2 the last segment would get a negative sample count (numpy.linspace raises
+ *   ValueError); 3 start and goal closer than 1e-6 (ValueError in compute_detour_waypoints).  X0/U0 of such agents are zeroed.
+ */
+int scvx_warm_start_batched(int model_id, int n_agents, int K, int M_max, const double* p0, const double* p1,
+                            const double* obs_c, const double* obs_r, const int* obs_count, double clearance,
+                            double* X0, double* U0, int* status, void* stream);
+
+/* scvx_min_inter_agent_distance -- replaces min_inter_agent_distance (SCvx/utils/analysis.py:10-31):
+ *   d_mat [n_agents][n_agents] (symmetric, zero diagonal) = min over k of || X_i[0:n_rows, k] - X_j[0:n_rows, k] ||_2;
+ *   d_min [1] = smallest strictly positive entry (+inf when there is none: the reference raises on an empty selection).
+ *   X [n_agents][n_x][K]; the reference always takes n_rows = 3 (for the unicycle that includes the heading row).
+ * scvx_min_agent_obstacle_distance -- replaces min_agent_obstacle_distance (analysis.py:34-62):
+ *   d_mat [n_agents][M] = min over k of || X_i[0:n_rows, k] - c_j || - (robot_radius + r_j); d_min [1] = its minimum
+ *   (+inf when n_agents*M == 0).  obs_c [M][n_rows], obs_r [M]. */
+int scvx_min_inter_agent_distance(int n_agents, int K, int n_x, int n_rows, const double* X, double* d_mat, double* d_min,
+                                  void* stream);
+int scvx_min_agent_obstacle_distance(int n_agents, int K, int n_x, int n_rows, int M, const double* X, const double* obs_c,
+                                     const double* obs_r, double robot_radius, double* d_mat, double* d_min, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py only; not on the product path).
  * scvx_probe_fp64: `blocks` x 256 threads x `iters` x 8 independent DFMA; *flops_h (HOST pointer) receives the flop
  * count of the launch; `out` needs blocks*256 doubles.  scvx_l2_flush: write sweep over a buffer (> L2) between timed steps.
