@@ -138,7 +138,7 @@ class SubproblemWorkspace:
 def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_radius, x_init, x_final, pos_lo,
                      pos_hi, v_max, w_max, obs_a, obs_b, weight_nu, weight_slack, weight_sigma,
                      col_a=None, col_b=None, col_mask=None, quad_rho=None, lin_p=None, weight_col=1e5,
-                     max_iter=0, norm1_induced=True):
+                     max_iter=0, norm1_induced=True, quad_diag=None, lin_w=None, quad_pair=None, fix_sigma=False):
     """SCProblem.solve / AgentSolver.solve for a batch (sc_problem.py:15-105, agent_solver.py:43-117).
     Results land in the workspace's output tensors."""
     a = SolveArgs()
@@ -160,6 +160,7 @@ def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_
     a.obs_a, a.obs_b = (P(obs_a), P(obs_b)) if ws.M else (None, None)
     a.col_a, a.col_b, a.col_mask = P(col_a), P(col_b), P(col_mask)
     a.quad_rho, a.lin_p = P(quad_rho), P(lin_p)
+    a.quad_diag, a.lin_w, a.quad_pair, a.fix_sigma = P(quad_diag), P(lin_w), P(quad_pair), 1 if fix_sigma else 0
     a.weight_nu, a.weight_slack, a.weight_sigma, a.weight_col = float(weight_nu), float(weight_slack), float(weight_sigma), float(weight_col)
     a.X, a.U, a.nu, a.sigma = ptr(ws.X), ptr(ws.U), ptr(ws.nu), ptr(ws.sigma)
     a.s_prime = ptr(ws.s_prime) if ws.M else None
@@ -220,3 +221,22 @@ def min_agent_obstacle_distance(X, obs_c, obs_r, robot_radius, n_rows=3):
                                                   ptr(obs_r) if M else None, float(robot_radius), ptr(d_mat), ptr(d_min),
                                                   stream_ptr()), "scvx_min_agent_obstacle_distance")
     return d_min, d_mat
+
+
+def slab_normals(model_id, P_own, X_dir, X_off, radius, i0=0, out=None):
+    """Slab rows of the Nash best response (game_model.py:56-67,118-124) for local agents i0..i0+n_local-1.
+    P_own (n_local, n_x, K); X_dir, X_off (n_agents, n_x, K); radius (n_local,) ->
+    col_a (n_local, n_agents, d, K), col_b (n_local, n_agents, K), degenerate (n_local,) int32."""
+    _, _, d = MODEL_DIMS[model_id]
+    P_own, X_dir, X_off, radius = _dev(P_own), _dev(X_dir), _dev(X_off), _dev(radius)
+    n_local, _, K = P_own.shape
+    n_agents = X_dir.shape[0]
+    assert X_off.shape == X_dir.shape and radius.shape == (n_local,)
+    if out is None:
+        out = (torch.empty((n_local, n_agents, d, K), dtype=F64, device=P_own.device),
+               torch.empty((n_local, n_agents, K), dtype=F64, device=P_own.device))
+    a, b = out
+    deg = torch.empty((n_local,), dtype=torch.int32, device=P_own.device)
+    check(load().scvx_slab_normals_batched(model_id, n_local, i0, n_agents, K, ptr(radius), ptr(P_own), ptr(X_dir),
+                                           ptr(X_off), ptr(a), ptr(b), ptr(deg), stream_ptr()), "scvx_slab_normals_batched")
+    return a, b, deg

@@ -177,6 +177,50 @@ outer_update_kernel(int K, int n_x, int n_u, int M, double conv_tol, const doubl
   }
 }
 
+
+// Slab normals of the Nash best response (GameUnicycleModel.update_slabs + the slab rows of get_cost_function,
+// SCvx/models/game_model.py:56-67,118-124):  z_jk = d / ||d||, d = p_ik - q_jk  (zero when ||d|| < 1e-6, no +1e-6 in the
+// denominator), row  z_jk.(p_ik - Y_jk) >= radius_i  <=>  a.p >= b  with a = z, b = radius_i + z.Y_jk.
+// degenerate[i] counts the (j, k) whose normal vanished: the reference's row 0 >= radius is infeasible there.
+template <int D>
+__global__ void __launch_bounds__(128)
+slab_normals_kernel(int n_local, int i0, int n_agents, int K, int n_x, const double* __restrict__ radius,
+                    const double* __restrict__ P_own, const double* __restrict__ X_dir, const double* __restrict__ X_off,
+                    double* __restrict__ col_a, double* __restrict__ col_b, int* __restrict__ degenerate) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.z;
+  if (k >= K) return;
+  double p[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) p[c] = P_own[((size_t)i * n_x + c) * K + k];
+  const int j0 = blockIdx.y * 16;
+  const int j1 = min(j0 + 16, n_agents);
+  int bad = 0;
+  for (int j = j0; j < j1; ++j) {
+    const size_t slot = (size_t)i * n_agents + j;
+    double z[D], n2 = 0.0, zy = 0.0;
+    if (j == i0 + i) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) col_a[(slot * D + c) * K + k] = 0.0;
+      col_b[slot * K + k] = 0.0;
+      continue;
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) { z[c] = p[c] - X_dir[((size_t)j * n_x + c) * K + k]; n2 = (c == 0) ? __dmul_rn(z[c], z[c]) : __dadd_rn(n2, __dmul_rn(z[c], z[c])); }
+    const double nrm = sqrt(n2);
+    const bool zero = nrm < 1e-6;
+    bad += zero ? 1 : 0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      z[c] = zero ? 0.0 : z[c] / nrm;
+      col_a[(slot * D + c) * K + k] = z[c];
+      zy += z[c] * X_off[((size_t)j * n_x + c) * K + k];
+    }
+    col_b[slot * K + k] = radius[i] + zy;
+  }
+  if (bad && degenerate) atomicAdd(degenerate + i, bad);
+}
+
 }  // namespace scvx
 
 using namespace scvx;
@@ -217,6 +261,29 @@ extern "C" int scvx_linearize_collision_batched(int model_id, int n_local, int i
   else
     linearize_collision_kernel<3><<<grid, 128, 0, st>>>(n_local, i0, n_agents, K, nx, d_min, X_own, X_nbr, col_a, col_b);
   SCVX_CHECK_LAUNCH("scvx_linearize_collision_batched");
+  return SCVX_OK;
+}
+
+extern "C" int scvx_slab_normals_batched(int model_id, int n_local, int i0, int n_agents, int K, const double* radius,
+                                         const double* P_own, const double* X_dir, const double* X_off, double* col_a,
+                                         double* col_b, int* degenerate, void* stream) {
+  int nx, nu, d;
+  if (!model_dims(model_id, &nx, &nu, &d)) return bad_arg("model_id");
+  if (n_local < 0 || n_agents < 0 || K < 1 || i0 < 0) return bad_arg("n_local/n_agents/K/i0");
+  if (n_local == 0 || n_agents == 0) return SCVX_OK;
+  if (n_local > 65535) return bad_arg("n_local > 65535 (split the call)");
+  if (!radius || !P_own || !X_dir || !X_off || !col_a || !col_b) return bad_arg("null pointer");
+  dim3 grid((K + 127) / 128, (n_agents + 15) / 16, n_local);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (degenerate) {
+    cudaError_t e = cudaMemsetAsync(degenerate, 0, (size_t)n_local * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  }
+  if (d == 2)
+    slab_normals_kernel<2><<<grid, 128, 0, st>>>(n_local, i0, n_agents, K, nx, radius, P_own, X_dir, X_off, col_a, col_b, degenerate);
+  else
+    slab_normals_kernel<3><<<grid, 128, 0, st>>>(n_local, i0, n_agents, K, nx, radius, P_own, X_dir, X_off, col_a, col_b, degenerate);
+  SCVX_CHECK_LAUNCH("scvx_slab_normals_batched");
   return SCVX_OK;
 }
 

@@ -599,12 +599,29 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
   sc.qrho = a.quad_rho ? a.quad_rho[agent] * sc.cs : 0.0;
   sc.hw_obs = a.weight_slack * sc.cs; sc.hw_col = a.weight_col * sc.cs;
   const double* qlin = a.lin_p ? a.lin_p + (size_t)agent * D * K : nullptr;
+  // best-response terms (all absent for the plain problems): diagonal / linear / consecutive-difference quadratics
+  const double* qdiag = a.quad_diag ? a.quad_diag + (size_t)agent * NS : nullptr;
+  const double* qpair = a.quad_pair ? a.quad_pair + (size_t)agent * NS : nullptr;
+  const double* qlinw = a.lin_w ? a.lin_w + (size_t)agent * NS * K : nullptr;
+  const bool game = qdiag || qpair || qlinw;
+  const bool fix_sig = a.fix_sigma != 0;
+  // gradient and curvature of the smooth extra cost at stage k, component i (scaled); obj: this stage's share of the value
+  auto game_terms = [&](int k, int i, const double* w, double& grad, double& curv, double& obj) {
+    grad = 0.0; curv = 0.0; obj = 0.0;
+    if (qdiag) { const double q = qdiag[i] * sc.cs; grad += q * w[i]; curv += q; obj += 0.5 * q * w[i] * w[i]; }
+    if (qlinw) { const double l = qlinw[(size_t)i * K + k] * sc.cs; grad += l; obj += l * w[i]; }
+    if (qpair) {
+      const double c = qpair[i] * sc.cs;
+      if (k > 0) { const double dlt = w[i] - w[i - NSP]; grad += c * dlt; curv += c; }
+      if (k < K - 1) { const double dlt = w[i + NSP] - w[i]; grad -= c * dlt; curv += c; obj += 0.5 * c * dlt * dlt; }
+    }
+  };
   const double* obs_a = a.obs_a ? a.obs_a + (size_t)agent * Mobs * D * K : nullptr;
   const double* obs_b = a.obs_b ? a.obs_b + (size_t)agent * Mobs * K : nullptr;
   const double* col_a = a.col_a ? a.col_a + (size_t)agent * a.n_nbr * D * K : nullptr;
   const double* col_b = a.col_b ? a.col_b + (size_t)agent * a.n_nbr * K : nullptr;
   const unsigned char* col_mask = a.col_mask ? a.col_mask + (size_t)agent * a.n_nbr : nullptr;
-  const bool coupled = (sc.qrho > 0.0) || BALL;          // common primal/dual step length
+  const bool coupled = (sc.qrho > 0.0) || BALL || game;  // common primal/dual step length
 
   AgentPtrs ws;
   {
@@ -698,7 +715,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
   __syncthreads();
   {
     // t_nu, t_x, t_u from maxima over stages
-    const double sig0 = fmax(sc.sig_ref, fmin(1e-2, sc.r_tr / 16.0));
+    const double sig0 = fix_sig ? sc.sig_ref : fmax(sc.sig_ref, fmin(1e-2, sc.r_tr / 16.0));
     double v[3] = {0.0, 0.0, 0.0};
     for (int k = tid; k < K; k += nthr) {
       const double* w = W + k * NSP;
@@ -1006,6 +1023,14 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         Dl[c][c] += sc.qrho;
         part[17] += 0.5 * sc.qrho * w[c] * w[c] + ql * w[c];
       }
+      if (game) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          double g, cv, ob;
+          game_terms(k, i, w, g, cv, ob);
+          bt[i] += g; bl[i] += g; Dl[i][i] += cv; part[17] += ob;
+        }
+      }
       // write own-stage pieces (interval pieces are added after the barrier)
       double* dk = Dk + (size_t)k * SD;
 #pragma unroll
@@ -1071,6 +1096,10 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
           for (int i = 0; i < NS; ++i)
 #pragma unroll
             for (int j = 0; j < NS; ++j) ek[i * NS + j] = Jn[0][i] * T[0][j] + Jn[1][i] * T[1][j] + Jn[2][i] * T[2][j];
+          if (qpair) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ek[i * NS + i] -= qpair[i] * sc.cs;
+          }
         } else {
 #pragma unroll
           for (int i = 0; i < NS * NS; ++i) ek[i] = 0.0;
@@ -1126,6 +1155,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
       for (int i = 0; i < NS; ++i) {
         dW[k * NSP + i] = -acc_t[i];
         rdmax = fmax(rdmax, fabs(acc_l[i]));
+        if (fix_sig) rb[i] = 0.0;
       }
     }
     // E_k for k = 0 is zero (stage 0 fixed) -- written by the !fr branch.  Reduce the partials.
@@ -1160,6 +1190,11 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
         }
       }
       bg[0] += sc.c_sig; bg[1] += sc.c_tnu; rdg[0] += sc.c_sig; rdg[1] += sc.c_tnu;
+      if (fix_sig) {       // sigma == sigma_ref: unit row/column, zero right-hand side, no stationarity condition
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { Gg[0][i] = 0.0; Gg[i][0] = 0.0; }
+        Gg[0][0] = 1.0; bg[0] = 0.0; rdg[0] = 0.0;
+      }
       double rd_inf = fmax(red[2], red[18]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) { rd_inf = fmax(rd_inf, fabs(rdg[c])); gl[34 + c] = -bg[c]; }
@@ -1482,6 +1517,14 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
             const double ql = qlin ? qlin[(size_t)c * K + k] * sc.cs : 0.0;
             bt[c] += sc.qrho * w[c] + ql;
           }
+          if (game) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+              double g, cv, ob;
+              game_terms(k, i, w, g, cv, ob);
+              bt[i] += g;
+            }
+          }
           // stash own-stage rhs piece; interval pieces are added after the barrier (dW is free: the affine
           // direction lives in dWa)
 #pragma unroll
@@ -1549,6 +1592,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
             for (int i = 0; i < 4; ++i) bg[i] += gG(r, i) * tau;
           }
           bg[0] += sc.c_sig; bg[1] += sc.c_tnu;
+          if (fix_sig) bg[0] = 0.0;
 #pragma unroll
           for (int c = 0; c < 4; ++c) gl[34 + c] = -bg[c];
         }
@@ -1677,6 +1721,14 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
       for (int c = 0; c < D; ++c) {
         const double ql = qlin ? qlin[(size_t)c * K + k] : 0.0;
         pr[3] += 0.5 * (a.quad_rho ? a.quad_rho[agent] : 0.0) * w[c] * w[c] + ql * w[c];
+      }
+      if (game) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+          double g, cv, ob;
+          game_terms(k, i, w, g, cv, ob);
+          pr[3] += ob / sc.cs;
+        }
       }
     }
     const int ops[4] = {2, 0, 0, 0};

@@ -97,7 +97,8 @@ class SCProblem:
         a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(shape if shape else (1,)))
         return torch.as_tensor(a).to(self._batch.device).unsqueeze(0) if shape else torch.as_tensor(a).to(self._batch.device)
 
-    def _solve_device(self, max_iter=0, col_a=None, col_b=None, quad_rho=None, lin_p=None, weight_col=1e5):
+    def _solve_device(self, max_iter=0, col_a=None, col_b=None, quad_rho=None, lin_p=None, weight_col=1e5,
+                      quad_diag=None, lin_w=None, quad_pair=None, fix_sigma=False):
         b = self._batch
         n_nbr = 0 if col_a is None else col_a.shape[1]
         ws = self._ws.get(n_nbr)
@@ -111,7 +112,8 @@ class SCProblem:
             ws, mats, X_ref, U_ref, self._dev("sigma_ref"), self._dev("tr_radius"), b.x_init, b.x_final,
             b.pos_lo, b.pos_hi, b.v_max, b.w_max, self._obs_a, self._obs_b,
             float(self.par["weight_nu"].value), float(self.par["weight_slack"].value), float(self.par["weight_sigma"].value),
-            col_a=col_a, col_b=col_b, quad_rho=quad_rho, lin_p=lin_p, weight_col=weight_col, max_iter=max_iter)
+            col_a=col_a, col_b=col_b, quad_rho=quad_rho, lin_p=lin_p, weight_col=weight_col, max_iter=max_iter,
+            quad_diag=quad_diag, lin_w=lin_w, quad_pair=quad_pair, fix_sigma=fix_sigma)
         self.var["X"].value = ws.X[0].cpu().numpy()
         self.var["U"].value = ws.U[0].cpu().numpy()
         self.var["nu"].value = ws.nu[0].cpu().numpy()

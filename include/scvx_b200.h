@@ -105,6 +105,16 @@ int scvx_linearize_collision_batched(int model_id, int n_local, int i0, int n_ag
                                      const double* X_own, const double* X_nbr,
                                      double* col_a, double* col_b, void* stream);
 
+/* Slab rows of the Nash best response: GameUnicycleModel.update_slabs (SCvx/models/game_model.py:56-67) and the rows
+ * z_jk.(p_ik - Y_jk) >= collision_radius of get_cost_function (game_model.py:118-124), in the half-space layout of
+ * scvx_linearize_collision_batched (a = z, b = radius + z.Y).  z_jk = (P_own_ik - X_dir_jk)/||.|| -- exactly zero when the
+ * norm is below 1e-6, as in the reference (no 1e-6 in the denominator).  radius [n_local]; P_own [n_local][n_x][K];
+ * X_dir, X_off [n_agents][n_x][K] (the neighbours' trajectories that give the direction resp. the offset Y);
+ * degenerate [n_local] or NULL: number of vanished normals per agent (the reference's problem is infeasible then). */
+int scvx_slab_normals_batched(int model_id, int n_local, int i0, int n_agents, int K, const double* radius,
+                              const double* P_own, const double* X_dir, const double* X_off, double* col_a,
+                              double* col_b, int* degenerate, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Stage 3 -- convex sub-problem, batched.
  * Replaces SCProblem.solve (SCvx/optimization/sc_problem.py:15-105, problem statement :21-83 with the
@@ -148,6 +158,16 @@ typedef struct scvx_solve_args {
   int *status, *iters;                            /* [n] */
   /* scratch */
   void* workspace; unsigned long long workspace_bytes;
+  /* Best-response (Nash game) terms -- AgentBestResponse.setup (SCvx/optimization/agent_best_response.py:36-100) with the
+   * cost of GameUnicycleModel.get_cost_function (SCvx/models/game_model.py:69-126); all NULL / 0 for the plain problems.
+   *   sum_k sum_i [ quad_diag_i/2 w_ik^2 + lin_w_ik w_ik ] + sum_{k<K-1} sum_i quad_pair_i/2 (w_i,k+1 - w_ik)^2,
+   *   w_k = (x_k, u_k), i over the n_x + n_u stage components: control effort c ||U||^2 -> quad_diag_u = 2c; inertia
+   *   c ||X - X_prev||^2 -> quad_diag_x = 2c, lin_w_x = -2c X_prev; control rate / curvature c sum (dw)^2 -> quad_pair = 2c.
+   * fix_sigma != 0 adds the constraint sigma == sigma_ref (agent_best_response.py:76-77): the sigma column is frozen. */
+  const double *quad_diag;                        /* [n][n_x+n_u] or NULL */
+  const double *lin_w;                            /* [n][n_x+n_u][K] or NULL */
+  const double *quad_pair;                        /* [n][n_x+n_u] or NULL */
+  int fix_sigma;
 } scvx_solve_args;
 
 /* bytes of device workspace scvx_solve_batched needs for these sizes */

@@ -47,6 +47,31 @@ class Params:
         self.neighbors = neighbors or []
         self.rho, self.d_min, self.weight_col = float(rho), float(d_min), float(weight_col)
         self.obs_a, self.obs_rhs, self.obs_c = linearize_obstacles(model, self.X_ref)
+        # Nash best response (agent_best_response.py:36-100, game_model.py:69-126); see set_game()
+        self.game = None
+
+    def set_game(self, quad_diag=None, lin_w=None, quad_pair=None, hard_rows=(), fix_sigma=True, const=0.0):
+        """Extra terms of AgentBestResponse: with w_k = (x_k, u_k),
+        sum_k sum_i [quad_diag_i/2 w_ik^2 + lin_w_ik w_ik] + sum_{k<K-1} sum_i quad_pair_i/2 (w_i,k+1 - w_ik)^2 + const,
+        hard slab rows a_k.p_k >= b_k (game_model.py:118-124) and sigma == sigma_ref (agent_best_response.py:76-77)."""
+        ns = self.model.n_x + self.model.n_u
+        z = lambda v, shape: np.zeros(shape) if v is None else np.asarray(v, float).reshape(shape)   # noqa: E731
+        self.game = {"qd": z(quad_diag, (ns,)), "lw": z(lin_w, (ns, self.K)), "qp": z(quad_pair, (ns,)),
+                     "rows": [(np.asarray(a, float), np.asarray(b, float)) for a, b in hard_rows],
+                     "fix_sigma": bool(fix_sigma), "const": float(const)}
+        return self
+
+    def game_cost(self, X, U):
+        """(value, gradient wrt W = vstack(X, U)) of the smooth extra cost."""
+        g = self.game
+        W = np.vstack([X, U])
+        val = 0.5 * (g["qd"][:, None] * W * W).sum() + (g["lw"] * W).sum() + g["const"]
+        grad = g["qd"][:, None] * W + g["lw"]
+        dW = W[:, 1:] - W[:, :-1]
+        val += 0.5 * (g["qp"][:, None] * dW * dW).sum()
+        grad[:, 1:] += g["qp"][:, None] * dW
+        grad[:, :-1] -= g["qp"][:, None] * dW
+        return float(val), grad
 
 
 # ---------------------------------------------------------------------------------------------
@@ -97,6 +122,12 @@ def evaluate(p: Params, X, U, sigma):
     viol = max(viol, (P - (m.upper_bound - m.robot_radius)).max(), ((m.lower_bound + m.robot_radius) - P).max())
     tr = norm1(X - p.X_ref, p.norm1_mode) + norm1(U - p.U_ref, p.norm1_mode) + abs(sigma - p.sigma_ref)
     viol = max(viol, tr - p.tr_radius, -sigma, 0.0)
+    if p.game is not None:
+        obj += p.game_cost(X, U)[0]
+        for a_h, b_h in p.game["rows"]:
+            viol = max(viol, (b_h - np.einsum("dk,dk->k", a_h, P)).max())
+        if p.game["fix_sigma"]:
+            viol = max(viol, abs(sigma - p.sigma_ref))
     return {"obj": float(obj), "viol": float(viol), "nu": nu, "s_prime": sprime, "S": S,
             "nu_norm": float(norm1(nu, "induced")), "slack_sum": float(sprime.sum()), "tr_lhs": float(tr)}
 
@@ -188,6 +219,13 @@ def solve(p: Params, solver="choose", max_cuts=60, linearize_at=None):
             a = nb["a"][:, k]
             b.row([X(i, k) for i in range(d)] + [iS + q * K + k], list(a) + [1.0],
                   p.d_min + a.dot(nb["Y"][:, k]), INF)
+    # hard slab rows of the Nash best response  z.(p_k - Y_k) >= r  <=>  a.p_k >= b   (game_model.py:118-124)
+    if p.game is not None:
+        for a_h, b_h in p.game["rows"]:
+            for k in range(K):
+                b.row([X(i, k) for i in range(d)], list(a_h[:, k]), float(b_h[k]), INF)
+        if p.game["fix_sigma"]:
+            lo[iSig] = hi[iSig] = p.sigma_ref
     # dynamics rows (sc_problem.py:53-68)
     for k in range(K - 1):
         A = p.A_bar[:, k].reshape((n_x, n_x), order="F")
@@ -253,6 +291,19 @@ def solve(p: Params, solver="choose", max_cuts=60, linearize_at=None):
                     c[X(i, k)] += p.rho * NB * P0[i, k]
             offset -= 0.5 * p.rho * NB * (P0 ** 2).sum()
 
+    if p.game is not None:
+        g = p.game
+        if linearize_at is None:
+            raise NotImplementedError("the Nash best response is certified through qp_bracket (LP lower bound)")
+        X0, U0 = linearize_at
+        val0, grad0 = p.game_cost(np.asarray(X0, float), np.asarray(U0, float))
+        W0 = np.vstack([X0, U0])
+        for k in range(K):
+            for i in range(n_x):
+                c[X(i, k)] += grad0[i, k]
+            for i in range(n_u):
+                c[Uv(i, k)] += grad0[n_x + i, k]
+        offset += val0 - float((grad0 * W0).sum())
     rows, cols, vals = list(b.rows), list(b.cols), list(b.vals)
     rlo, rhi = list(b.rlo), list(b.rhi)
     mrows = b.m
@@ -292,5 +343,5 @@ def qp_bracket(p: Params, X, U, sigma):
     of the LP obtained by linearising the quadratic term about z0 (Frank-Wolfe gap).  HiGHS' own QP
     active-set solver does not finish on these problems (>10 min at K=12), so QP parity is pinned this way."""
     f0 = evaluate(p, X, U, sigma)
-    lb = solve(p, linearize_at=X[0:p.model.d, :])
+    lb = solve(p, linearize_at=(X, U) if p.game is not None else X[0:p.model.d, :])
     return f0["obj"], lb["obj"], f0["viol"], lb["ok"]

@@ -27,7 +27,7 @@ def random_unicycle_scene(rng, M=8):
     return omodels.unicycle(r_init=start, r_final=goal, obstacles=obs)
 
 
-def solve_batch_on_gpu(params, dev, max_iter=0):
+def solve_batch_on_gpu(params, dev, max_iter=0, slab_penalty=1e6):
     """params: list of oracle Params with identical (model kind, K, M, number of neighbours).
     Returns the workspace (outputs as torch tensors)."""
     from scvx_b200 import _device
@@ -45,6 +45,14 @@ def solve_batch_on_gpu(params, dev, max_iter=0):
         col_b = st(lambda p: np.stack([p.d_min + np.einsum("dk,dk->k", nb["a"], nb["Y"]) for nb in p.neighbors]))
         quad = st(lambda p: np.array(p.rho * len(p.neighbors)))
         lin = st(lambda p: sum(nb["Lam"] - p.rho * nb["Y"] for nb in p.neighbors))
+    game_kw = {}
+    if p0.game is not None:        # Nash best response: slab rows ride in the neighbour slots with an exact penalty
+        NB = len(p0.game["rows"])
+        if NB:
+            col_a = st(lambda p: np.stack([a for a, _ in p.game["rows"]]))
+            col_b = st(lambda p: np.stack([b for _, b in p.game["rows"]]))
+        game_kw = dict(quad_diag=st(lambda p: p.game["qd"]), lin_w=st(lambda p: p.game["lw"]),
+                       quad_pair=st(lambda p: p.game["qp"]), fix_sigma=p0.game["fix_sigma"])
     ws = _device.SubproblemWorkspace(mid, n, K, M, NB, dev)
     _device.solve_subproblem(
         ws, mats, st(lambda p: p.X_ref), st(lambda p: p.U_ref), st(lambda p: np.array(p.sigma_ref)),
@@ -53,7 +61,8 @@ def solve_batch_on_gpu(params, dev, max_iter=0):
         st(lambda p: np.array(p.model.upper_bound - p.model.robot_radius)),
         st(lambda p: np.array(p.model.v_max)), st(lambda p: np.array(p.model.w_max)),
         obs_a, obs_b, p0.weight_nu, p0.weight_slack, p0.weight_sigma,
-        col_a=col_a, col_b=col_b, quad_rho=quad, lin_p=lin, weight_col=p0.weight_col, max_iter=max_iter)
+        col_a=col_a, col_b=col_b, quad_rho=quad, lin_p=lin, weight_col=(slab_penalty if p0.game is not None else p0.weight_col),
+        max_iter=max_iter, **game_kw)
     torch.cuda.synchronize()
     return ws
 

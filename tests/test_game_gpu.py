@@ -1,0 +1,138 @@
+"""Nash best response on the GPU (SURVEY section 8 f rank 1): the interior-point kernel with the GameUnicycleModel cost,
+frozen sigma and slab rows, against the exact-LP bracket of the oracle; the AgentBestResponse / NashSolver mirrors.
+
+Certificate (same device as the ADMM QP tests): for a convex objective, LB = optimum of the LP obtained by linearising the
+quadratic about the candidate satisfies LB <= f_opt <= f(candidate); the candidate is optimal to the accuracy f - LB."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import foh as ofoh, models as omodels, subproblem as ospb
+
+pytestmark = pytest.mark.gpu
+
+
+def _slabs(P_own, P_dir, P_off, radius):
+    d = P_own - P_dir
+    n = np.linalg.norm(d, axis=0)
+    z = np.where(n < 1e-6, 0.0, d / np.where(n < 1e-6, 1.0, n))
+    return z, radius + (z * P_off).sum(axis=0)
+
+
+def _game_problems(K, rng, n_agents=3):
+    """Best responses of agent 0 against n_agents-1 crossing neighbours (config/default_game.py layout, perturbed)."""
+    starts = [np.array([0.0, -1.0, 0.0]), np.array([2.0, -1.0, 0.0]), np.array([1.0, -1.5, 0.0])][:n_agents]
+    goals = [np.array([2.0, 3.0, 0.0]), np.array([0.0, 3.0, 0.0]), np.array([1.0, 3.5, 0.0])][:n_agents]
+    ms = [omodels.unicycle(r_init=s, r_final=g, obstacles=[([1.0, 1.0], 0.25), ([1.0, -0.3], 0.02)], bounds=(-5.0, 5.0))
+          for s, g in zip(starts, goals)]
+    XU = [m.initialize_trajectory(K) for m in ms]
+    out = []
+    for trial in range(3):
+        Xs = [x + (0.02 * rng.normal(size=x.shape) if trial else 0.0) for x, _ in XU]
+        for x, m in zip(Xs, ms):
+            x[:, 0], x[:, -1] = m.x_init, m.x_final
+        i = 0
+        # neighbours shifted sideways so that the slabs are feasible at the reference (as after an ACS update)
+        nbrs = [Xs[j].copy() for j in range(n_agents) if j != i]
+        for q, P in enumerate(nbrs):
+            P[0] += 0.8 * (1 if q % 2 == 0 else -1) * np.sin(np.linspace(0, np.pi, K))
+        mats = ofoh.OracleFOH(ms[i], K).calculate_discretization(Xs[i], XU[i][1], 6.0)
+        p = ospb.Params(ms[i], K, mats, Xs[i], XU[i][1], 6.0, 100.0)
+        rows = [_slabs(Xs[i][0:2], P[0:2], P[0:2], 0.3) for P in nbrs]
+        qd = np.array([0.0, 0.0, 0.0, 10.0, 10.0]); qp = np.array([0.0, 0.0, 200.0, 10.0, 10.0])
+        lw = np.zeros((5, K))
+        if trial == 2:      # inertia term
+            qd[:3] += 2 * 0.5; lw[:3] += -2 * 0.5 * Xs[i]
+        p.set_game(quad_diag=qd, lin_w=lw, quad_pair=qp, hard_rows=rows, const=0.5 * (Xs[i] ** 2).sum() if trial == 2 else 0.0)
+        out.append(p)
+    return out
+
+
+@pytest.mark.parametrize("K", [30, 50])
+def test_best_response_kernel_vs_lp_bracket(cuda, K):
+    rng = np.random.default_rng(K)
+    params = _game_problems(K, rng)
+    ws = helpers.solve_batch_on_gpu(params, cuda)
+    for i, p in enumerate(params):
+        X, U, s = ws.X[i].cpu().numpy(), ws.U[i].cpu().numpy(), ws.sigma[i].item()
+        assert ws.status[i].item() == 0, (i, ws.status[i].item(), ws.iters[i].item())
+        assert s == p.sigma_ref                                   # sigma == sigma_ref, exactly
+        assert ws.col_slack[i].max().item() <= 1e-9               # hard slab rows hold: exact penalty inactive
+        f0, lb, viol, ok = ospb.qp_bracket(p, X, U, s)
+        assert ok and viol <= 1e-8, (i, viol)
+        assert lb <= f0 * (1 + 1e-9) and f0 - lb <= 1e-6 * abs(f0), (i, f0, lb)
+        # the kernel's reported objective is the oracle's evaluation of its point
+        assert ws.objective[i].item() + p.game["const"] == pytest.approx(f0, rel=1e-10)
+
+
+def test_frozen_sigma_without_game_terms_matches_lp(cuda):
+    """fix_sigma alone (LP): exact HiGHS optimum with sigma pinned."""
+    m = omodels.unicycle()
+    K = 40
+    X, U = m.initialize_trajectory(K)
+    mats = ofoh.OracleFOH(m, K).calculate_discretization(X, U, 20.0)
+    p = ospb.Params(m, K, mats, X, U, 20.0, 100.0).set_game()
+    r = ospb.solve(p, linearize_at=(X, U))       # no quadratic: the "linearised" problem IS the problem
+    ws = helpers.solve_batch_on_gpu([p], cuda)
+    e = ospb.evaluate(p, ws.X[0].cpu().numpy(), ws.U[0].cpu().numpy(), ws.sigma[0].item())
+    assert ws.status[0].item() == 0 and ws.sigma[0].item() == 20.0
+    assert e["viol"] <= 1e-8 and abs(e["obj"] - r["obj"]) <= 1e-7 * abs(r["obj"])
+
+
+def test_slab_normals_kernel_vs_numpy(cuda):
+    from scvx_b200 import _device, _lib
+    rng = np.random.default_rng(2)
+    n, K = 5, 37
+    X = rng.normal(size=(n, 3, K)); Xd = rng.normal(size=(n, 3, K)); Xo = rng.normal(size=(n, 3, K))
+    Xd[2, :, 5] = X[1, :, 5]                                      # coincident pair (agent 1 vs neighbour 2, k = 5)
+    rad = rng.uniform(0.2, 0.6, n)
+    for mid, d in ((_lib.MODEL_UNICYCLE, 2), (_lib.MODEL_SINGLE_INTEGRATOR, 3)):
+        a, b, deg = _device.slab_normals(mid, helpers.to_dev(X, cuda), helpers.to_dev(Xd, cuda), helpers.to_dev(Xo, cuda),
+                                         helpers.to_dev(rad, cuda))
+        a, b, deg = a.cpu().numpy(), b.cpu().numpy(), deg.cpu().numpy()
+        for i in range(n):
+            for j in range(n):
+                if i == j:
+                    assert not a[i, j].any() and not b[i, j].any()
+                    continue
+                z, bb = _slabs(X[i, :d], Xd[j, :d], Xo[j, :d], rad[i])
+                np.testing.assert_allclose(a[i, j], z, rtol=0, atol=1e-15)
+                np.testing.assert_allclose(b[i, j], bb, rtol=0, atol=1e-14)
+        assert deg[1] == (1 if d == 3 else 0) or d == 2           # full 3-D coincidence only
+
+
+def test_nash_solver_mirror_two_agents(cuda):
+    """NashSolver.solve on the shipped two-agent game (config/default_game.py): literal Gauss-Seidel + ACS."""
+    from scvx_b200.models.game_model import GameUnicycleModel
+    from scvx_b200.models.multi_agent_model import MultiAgentModel
+    from scvx_b200.optimization.nash_solver import NashSolver
+    from scvx_b200.utils.analysis import min_inter_agent_distance
+    from scvx_b200.utils.initial_guess import initial_guess
+    K = 50
+    obstacles = [([1.0, 1.0], 0.25), ([1.0, -0.3], 0.02)]
+    agents = [dict(r_init=np.array([0.0, -1.0, 0.0]), r_final=np.array([2.0, 3.0, 0.0])),
+              dict(r_init=np.array([2.0, -1.0, 0.0]), r_final=np.array([0.0, 3.0, 0.0]))]
+    mam = MultiAgentModel([dict(a, obstacles=obstacles) for a in agents], d_min=0.5)
+    for idx, a in enumerate(agents):
+        mam.models[idx] = GameUnicycleModel(r_init=a["r_init"], r_final=a["r_final"], obstacles=obstacles, control_weight=5.0,
+                                            collision_radius=0.3, control_rate_weight=5.0, curvature_weight=100.0,
+                                            bounds=(-5.0, 5.0), robot_radius=0.1)
+    X_refs, U_refs = [], []
+    for a in agents:
+        X0, U0 = initial_guess(a["r_init"], a["r_final"], obstacles, 0.05, K)
+        X_refs.append(X0); U_refs.append(U0)
+    # the straight warm starts cross at the same knot: separate them in time as the reference's examples do not need to
+    X_refs[1][0] += 0.4 * np.sin(np.linspace(0, np.pi, K))
+    solver = NashSolver(mam, max_iter=3, tol=1e-3, K=K)
+    X_fin, U_fin, hist = solver.solve(X_refs, U_refs, sigma_ref=8.0)
+    assert len(hist) >= 1 and all(np.isfinite(h) for h in hist)
+    for a, X, U in zip(agents, X_fin, U_fin):
+        assert X.shape == (3, K) and U.shape == (2, K)
+        np.testing.assert_allclose(X[:, 0], a["r_init"], atol=1e-9); np.testing.assert_allclose(X[:, -1], a["r_final"], atol=1e-9)
+        assert (U[0] >= -1e-9).all() and (U[0] <= 1.0 + 1e-9).all()
+    # slab rows of the last best response hold at the knots: || p_1 - p_0 || >= z.(p_1 - p_0) >= collision_radius
+    sep = np.linalg.norm(X_fin[1][0:2] - X_fin[0][0:2], axis=0).min()
+    assert sep >= 0.3 - 1e-6, sep
+    d_min, _ = min_inter_agent_distance([np.vstack([x[0:2], np.zeros((1, K))]) for x in X_fin])
+    assert abs(d_min - sep) < 1e-12
