@@ -284,3 +284,124 @@ class BatchedADMM:
         return {"X": X_all, "U": U_all, "Y": Y, "Lambda": Lam,
                 "primal_hist": torch.stack(primal_hist).cpu().tolist(), "dual_hist": torch.stack(dual_hist).cpu().tolist(),
                 "objective": torch.stack(objs) if objs else None, "mask": mask}
+
+
+SLAB_PENALTY = 1e8               # exact-penalty weight of the hard slab rows (optimization/agent_best_response.py)
+SLAB_TOL = 1e-7
+
+
+class BatchedNash:
+    """Iterative best response (NashSolver.solve, SCvx/optimization/nash_solver.py:40-149) as JACOBI sweeps: every agent of
+    the local shard computes its best response -- with the ACS inner loop of slab-normal updates -- against the
+    trajectories of the previous sweep, all agents in one launch per step; one all-gather per sweep.  (The reference sweeps
+    Gauss-Seidel; agent 0's first best response is identical in both orders, which is what the parity test pins.)
+    """
+
+    def __init__(self, models, K, max_iter=20, tol=1e-3, max_acs_iters=5, acs_tol=1e-3, group=None, device=None,
+                 n_sub=0, ipm_max_iter=0):
+        import torch.distributed as dist
+        from .optimization.agent_best_response import game_tables
+        self.dist = dist if (group is not None or (dist.is_available() and dist.is_initialized())) else None
+        self.group = group
+        self.rank = self.dist.get_rank(group) if self.dist else 0
+        self.world = self.dist.get_world_size(group) if self.dist else 1
+        self.N, self.K = len(models), K
+        self.max_iter, self.tol, self.max_acs_iters, self.acs_tol = max_iter, tol, max_acs_iters, acs_tol
+        self.n_sub, self.ipm_max_iter = n_sub, ipm_max_iter
+        self.per, self.i0, self.i1 = shard_bounds(self.N, self.world, self.rank)
+        self.nl = self.i1 - self.i0
+        self.all = AgentBatch(models, K, device)
+        self.local = AgentBatch(models[self.i0:self.i1], K, device) if self.nl else None
+        self._tables = game_tables
+        b = self.all
+        dev = b.device
+        self.radius = torch.as_tensor(np.array([m.collision_radius for m in models[self.i0:self.i1]], dtype=np.float64)).to(dev)
+        self.inertia = [getattr(m, "inertia_weight", 0.0) for m in models[self.i0:self.i1]]
+        if self.nl:
+            lb = self.local
+            self.ws = _device.SubproblemWorkspace(lb.model_id, self.nl, K, lb.M, self.N, dev)
+            self.mats = tuple(torch.empty((self.nl, r, K - 1), dtype=F64, device=dev)
+                              for r in (b.n_x * b.n_x, b.n_x * b.n_u, b.n_x * b.n_u, b.n_x, b.n_x))
+            self.obs_a = torch.empty((self.nl, lb.M, b.d, K), dtype=F64, device=dev)
+            self.obs_b = torch.empty((self.nl, lb.M, K), dtype=F64, device=dev)
+            self.col_a = torch.empty((self.nl, self.N, b.d, K), dtype=F64, device=dev)
+            self.col_b = torch.empty((self.nl, self.N, K), dtype=F64, device=dev)
+            self.mask = torch.ones((self.nl, self.N), dtype=torch.uint8, device=dev)
+            self.mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
+        self.launches = 0
+
+    def _cost_tables(self, X_prev_local):
+        """quad_diag (nl, ns), lin_w (nl, ns, K), quad_pair (nl, ns), const (nl,) of the local agents."""
+        b = self.all
+        Xp = X_prev_local.cpu().numpy() if any(w > 0 for w in self.inertia) else None
+        qd, lw, qp, cst = [], [], [], []
+        for q, m in enumerate(self.local.models):
+            t = self._tables(m, Xp[q] if Xp is not None else np.zeros((b.n_x, self.K)), self.K, b.n_x, b.n_u)
+            qd.append(t[0]); lw.append(t[1]); qp.append(t[2]); cst.append(t[3])
+        up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(b.device)   # noqa: E731
+        return up(np.stack(qd)), up(np.stack(lw)), up(np.stack(qp)), up(np.array(cst))
+
+    def solve(self, X_refs, U_refs, sigma_ref=1.0):
+        """X_refs (N, n_x, K), U_refs (N, n_u, K) device tensors on every rank.  Returns dict(X, U, change_hist,
+        acs_iters (sweeps, nl), infeasible (sweeps, nl): residual slab slack or vanished normal -- the cases in which the
+        reference raises)."""
+        b = self.all
+        dev, K, N = b.device, self.K, self.N
+        X_all = _device._dev(X_refs).clone(); U_all = _device._dev(U_refs).clone()
+        sig = torch.full((max(self.nl, 1),), float(sigma_ref), dtype=F64, device=dev)[:self.nl]
+        tr = torch.full((max(self.nl, 1),), float(TRUST_RADIUS0), dtype=F64, device=dev)[:self.nl]
+        change_hist, acs_hist, bad_hist, obj_hist = [], [], [], []
+        for _ in range(self.max_iter):
+            if self.nl:
+                lb = self.local
+                X_loc = X_all[self.i0:self.i1].contiguous(); U_loc = U_all[self.i0:self.i1].contiguous()
+                _device.foh(lb.model_id, X_loc, U_loc, sig, self.n_sub, out=self.mats)
+                if lb.M:
+                    _device.linearize_obstacles(lb.model_id, X_loc, lb.obs_c, lb.obs_clear, out=(self.obs_a, self.obs_b))
+                qd, lw, qp, cst = self._cost_tables(X_loc)
+                # normals along X_prev -> neighbour_prev (agent_best_response.py:66-72); offsets use the neighbours' positions
+                _, _, deg = _device.slab_normals(lb.model_id, X_loc, X_all, X_all, self.radius, i0=self.i0,
+                                                 out=(self.col_a, self.col_b))
+                X_new = X_loc.clone(); U_new = U_loc.clone()
+                done = torch.zeros(self.nl, dtype=torch.bool, device=dev)
+                acs = torch.zeros(self.nl, dtype=torch.int32, device=dev)
+                bad = deg > 0
+                obj = torch.zeros(self.nl, dtype=F64, device=dev)
+                for _a in range(self.max_acs_iters):
+                    _device.solve_subproblem(self.ws, self.mats, X_loc, U_loc, sig, tr, lb.x_init, lb.x_final, lb.pos_lo,
+                                             lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU, WEIGHT_SLACK,
+                                             WEIGHT_SIGMA, col_a=self.col_a, col_b=self.col_b, col_mask=self.mask,
+                                             weight_col=SLAB_PENALTY, max_iter=self.ipm_max_iter, quad_diag=qd, lin_w=lw,
+                                             quad_pair=qp, fix_sigma=True)
+                    self.launches += 1
+                    live = ~done
+                    X_new[live] = self.ws.X[live]; U_new[live] = self.ws.U[live]
+                    obj[live] = self.ws.objective[live] + cst[live]
+                    slack = (self.ws.col_slack * self.mask[:, :, None]).amax(dim=(1, 2)) if N > 1 else torch.zeros(self.nl, device=dev, dtype=F64)
+                    bad |= live & ((slack > SLAB_TOL) | (self.ws.status == 2))
+                    acs += live.to(torch.int32)
+                    # dual update: normals along (new own position) - (neighbours' current positions)
+                    _, _, deg = _device.slab_normals(lb.model_id, X_new, X_all, X_all, self.radius, i0=self.i0,
+                                                     out=(self.col_a, self.col_b))
+                    bad |= deg > 0
+                    done |= torch.linalg.norm((X_new - X_loc).reshape(self.nl, -1), dim=1) < self.acs_tol
+                    if bool(done.all().item()):
+                        break
+                delta = torch.linalg.norm((X_new - X_loc).reshape(self.nl, -1), dim=1)
+                acs_hist.append(acs); bad_hist.append(bad.clone()); obj_hist.append(obj)
+            else:
+                X_new = torch.empty((0, b.n_x, K), dtype=F64, device=dev); U_new = torch.empty((0, b.n_u, K), dtype=F64, device=dev)
+                delta = torch.zeros(0, dtype=F64, device=dev)
+            mx = delta.max() if self.nl else torch.zeros((), dtype=F64, device=dev)
+            if self.dist and self.world > 1:
+                mx = mx.clone()
+                self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX, group=self.group)
+            X_all, U_all = allgather_shards(X_new, U_new, N, self.per, self.dist, self.group)
+            X_all, U_all = X_all.clone(), U_all.clone()
+            change_hist.append(float(mx.item()))
+            if change_hist[-1] < self.tol:
+                break
+        return {"X": X_all, "U": U_all, "change_hist": change_hist,
+                "acs_iters": torch.stack(acs_hist) if acs_hist else None,
+                "infeasible": torch.stack(bad_hist) if bad_hist else None,
+                "objective": torch.stack(obj_hist) if obj_hist else None}

@@ -15,7 +15,7 @@ from ..discretization.first_order_hold import FirstOrderHold
 from ..global_parameters import TRUST_RADIUS0, WEIGHT_NU, WEIGHT_SIGMA, WEIGHT_SLACK, K
 from .sc_problem import SCProblem, _Holder
 
-SLAB_PENALTY = 1e6          # exact-penalty weight of the hard slab rows (same scale as WEIGHT_SLACK)
+SLAB_PENALTY = 1e8          # exact-penalty weight of the hard slab rows: must dominate WEIGHT_SLACK (soft obstacle rows)
 SLAB_TOL = 1e-7             # a larger residual slack means the hard rows are infeasible
 
 

@@ -27,7 +27,7 @@ def random_unicycle_scene(rng, M=8):
     return omodels.unicycle(r_init=start, r_final=goal, obstacles=obs)
 
 
-def solve_batch_on_gpu(params, dev, max_iter=0, slab_penalty=1e6):
+def solve_batch_on_gpu(params, dev, max_iter=0, slab_penalty=1e8):
     """params: list of oracle Params with identical (model kind, K, M, number of neighbours).
     Returns the workspace (outputs as torch tensors)."""
     from scvx_b200 import _device
