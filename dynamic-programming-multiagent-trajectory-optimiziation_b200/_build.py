@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscvx_b200.so")
-SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "lti_qp.cu", "utils.cu", "probe.cu"]
+SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "lti_qp.cu", "utils.cu", "intersample.cu", "probe.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 

@@ -240,3 +240,37 @@ def slab_normals(model_id, P_own, X_dir, X_off, radius, i0=0, out=None):
     check(load().scvx_slab_normals_batched(model_id, n_local, i0, n_agents, K, ptr(radius), ptr(P_own), ptr(X_dir),
                                            ptr(X_off), ptr(a), ptr(b), ptr(deg), stream_ptr()), "scvx_slab_normals_batched")
     return a, b, deg
+
+
+def intersample(model_id, X, U, sigma, obs_c, obs_r, proj_dim=None, t_range=1.0, num_samples=100, eps=1e-4, tol=1e-6,
+                max_roots=4):
+    """find_critical_times + linearize_h (intersample_collision.py:29-97) for every (agent, segment, obstacle).
+    X (n, n_x, K), U (n, n_u, K), sigma (n,), obs_c (n, M, m), obs_r (n, M) ->
+    n_roots (n, K-1, M) int32, t_star, h0 (n, K-1, M, max_roots), grad_x (n, K-1, M, max_roots, n_x)."""
+    n_x, n_u, _ = MODEL_DIMS[model_id]
+    X, U, sigma, obs_c, obs_r = _dev(X), _dev(U), _dev(sigma), _dev(obs_c), _dev(obs_r)
+    n, _, K = X.shape
+    M = obs_c.shape[1]
+    m = obs_c.shape[2] if proj_dim is None else proj_dim
+    assert obs_c.shape == (n, M, m) and obs_r.shape == (n, M)
+    dev = X.device
+    n_roots = torch.zeros((n, K - 1, M), dtype=torch.int32, device=dev)
+    t_star = torch.full((n, K - 1, M, max_roots), float("nan"), dtype=F64, device=dev)
+    h0 = torch.full((n, K - 1, M, max_roots), float("nan"), dtype=F64, device=dev)
+    grad_x = torch.full((n, K - 1, M, max_roots, n_x), float("nan"), dtype=F64, device=dev)
+    check(load().scvx_intersample_batched(model_id, n, K, M, m, ptr(X), ptr(U), ptr(sigma), ptr(obs_c), ptr(obs_r),
+                                          float(t_range), int(num_samples), float(eps), float(tol), int(max_roots),
+                                          ptr(n_roots), ptr(t_star), ptr(h0), ptr(grad_x), stream_ptr()),
+          "scvx_intersample_batched")
+    return n_roots, t_star, h0, grad_x
+
+
+def clearance_samples(model_id, X, U, sigma, obs_c, total_r, resolution=50):
+    """h at t = i/resolution of every segment, one obstacle per agent: (n, K-1, resolution)."""
+    X, U, sigma, obs_c, total_r = _dev(X), _dev(U), _dev(sigma), _dev(obs_c), _dev(total_r)
+    n, _, K = X.shape
+    m = obs_c.shape[1]
+    out = torch.empty((n, K - 1, resolution), dtype=F64, device=X.device)
+    check(load().scvx_clearance_samples_batched(model_id, n, K, m, int(resolution), ptr(X), ptr(U), ptr(sigma), ptr(obs_c),
+                                                ptr(total_r), ptr(out), stream_ptr()), "scvx_clearance_samples_batched")
+    return out

@@ -72,6 +72,8 @@ SIGNATURES = {
     "scvx_warm_start_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 5 + [_c_dbl] + [_c_dp] * 3 + [_c_dp]),
     "scvx_min_inter_agent_distance": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 3 + [_c_dp]),
     "scvx_min_agent_obstacle_distance": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int] + [_c_dp] * 3 + [_c_dbl] + [_c_dp] * 2 + [_c_dp]),
+    "scvx_intersample_batched": (_c_int, [_c_int] * 5 + [_c_dp] * 5 + [_c_dbl, _c_int, _c_dbl, _c_dbl, _c_int] + [_c_dp] * 4 + [_c_dp]),
+    "scvx_clearance_samples_batched": (_c_int, [_c_int] * 5 + [_c_dp] * 6 + [_c_dp]),
     "scvx_probe_fp64": (_c_int, [_c_int, _c_int, _c_dp, ctypes.POINTER(_c_dbl), _c_dp]),
     "scvx_l2_flush": (_c_int, [_c_dp, ctypes.c_ulonglong, _c_dp]),
     "scvx_debug_phase_cycles": (_c_int, [ctypes.POINTER(ctypes.c_ulonglong), _c_int]),

@@ -259,6 +259,25 @@ int scvx_min_inter_agent_distance(int n_agents, int K, int n_x, int n_rows, cons
 int scvx_min_agent_obstacle_distance(int n_agents, int K, int n_x, int n_rows, int M, const double* X, const double* obs_c,
                                      const double* obs_r, double robot_radius, double* d_mat, double* d_min, void* stream);
 
+/* scvx_intersample_batched -- inter-sample obstacle clearance (SURVEY 8 f rank 3) for the segment flow of make_segment_f
+ * (SCvx/utils/intersample_collision.py:100-125): per (agent, segment k, obstacle j) the interior minima t* of
+ * h(t) = || x(t)[0:proj_dim] - c_j || - r_j found as find_critical_times does (:29-72: central-difference phi on a grid of
+ * num_samples points of [eps, t_range - eps], sign changes, <= 30 bisections to |b - a| < tol, keep 0 < t* < t_range with
+ * phi2 > 0), and at each t* the linearisation of linearize_h (:75-97): h0 and the central-difference gradient in x_k
+ * (grad_u is identically zero in the reference: the segment flow ignores its control argument).
+ *   X [n][n_x][K], U [n][n_u][K], sigma [n] (the reference passes sigma = 1.0), obs_c [n][M][proj_dim], obs_r [n][M];
+ *   items are ordered [agent][segment][obstacle]; n_roots [items] (may exceed max_roots: the rest is dropped);
+ *   t_star, h0 [items][max_roots]; grad_x [items][max_roots][n_x].
+ * scvx_clearance_samples_batched -- h at t = i/resolution, i < resolution, of every segment for one obstacle per agent
+ * (the intent of compute_intersample_clearance, SCvx/utils/analysis.py:64-104): h_cont [n][K-1][resolution]. */
+int scvx_intersample_batched(int model_id, int n_agents, int K, int M, int proj_dim, const double* X, const double* U,
+                             const double* sigma, const double* obs_c, const double* obs_r, double t_range, int num_samples,
+                             double eps, double tol, int max_roots, int* n_roots, double* t_star, double* h0, double* grad_x,
+                             void* stream);
+int scvx_clearance_samples_batched(int model_id, int n_agents, int K, int proj_dim, int resolution, const double* X,
+                                   const double* U, const double* sigma, const double* obs_c, const double* total_r,
+                                   double* h_cont, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Measurement helpers (bench.py only; not on the product path).
  * scvx_probe_fp64: `blocks` x 256 threads x `iters` x 8 independent DFMA; *flops_h (HOST pointer) receives the flop
