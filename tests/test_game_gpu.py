@@ -194,3 +194,39 @@ def test_batched_nash_converges_and_keeps_separation(cuda):
     for a, x in zip(agents, X):
         np.testing.assert_allclose(x[:, 0], a["r_init"], atol=1e-9); np.testing.assert_allclose(x[:, -1], a["r_final"], atol=1e-9)
     assert (out["acs_iters"] >= 1).all() and (out["acs_iters"] <= 5).all()
+
+
+def test_si_best_response_vs_bracket_and_si_nash_mirror(cuda):
+    """Single-integrator game: SOCP + quadratic costs + frozen sigma (the sub-problem the reference effectively solves)."""
+    K = 30
+    m = omodels.single_integrator(r_init=[-4.0, -4.0, -4.0], r_final=[4.0, 4.0, 4.0], obstacles=[([0.0, 0.5, 0.0], 1.0)])
+    X, U = m.initialize_trajectory(K)
+    mats = ofoh.OracleFOH(m, K).calculate_discretization(X, U, 16.0)
+    p = ospb.Params(m, K, mats, X, U, 16.0, 100.0)
+    qd = np.array([0.4, 0.4, 0.4, 2.0, 2.0, 2.0]); qp = np.array([0.0, 0.0, 0.0, 10.0, 10.0, 10.0])
+    lw = np.zeros((6, K)); lw[:3] = -0.4 * X
+    p.set_game(quad_diag=qd, lin_w=lw, quad_pair=qp, const=0.2 * (X ** 2).sum())
+    ws = helpers.solve_batch_on_gpu([p], cuda)
+    Xg, Ug, s = ws.X[0].cpu().numpy(), ws.U[0].cpu().numpy(), ws.sigma[0].item()
+    assert ws.status[0].item() == 0 and s == 16.0
+    f0, lb, viol, ok = ospb.qp_bracket(p, Xg, Ug, s)
+    assert ok and viol <= 1e-8 and f0 - lb <= 2e-6 * abs(f0), (f0, lb, viol)
+    # the mirror classes
+    from scvx_b200.models.game_si_model import GameSIModel
+    from scvx_b200.models.SI_multi_agent_model import SI_MultiAgentModel
+    from scvx_b200.optimization.si_nash_solver import SI_NashSolver
+    from scvx_b200.utils.IS_initial_guess import initial_guess
+    ends = [(np.array([-4.0, -4.0, -4.0]), np.array([4.0, 4.0, 4.0])), (np.array([4.0, -4.0, -3.0]), np.array([-4.0, 4.0, 3.0]))]
+    obstacles = [([0.0, 0.5, 0.0], 1.0)]
+    mam = SI_MultiAgentModel([dict(r_init=a, r_final=b, obstacles=obstacles) for a, b in ends], d_min=0.5)
+    mam.models = [GameSIModel(r_init=a, r_final=b, obstacles=obstacles, control_weight=1.0, control_rate_weight=5.0,
+                              inertia_weight=0.1) for a, b in ends]
+    X_refs, U_refs = zip(*[initial_guess(a, b, obstacles, 0.3, K) for a, b in ends])
+    X_fin, U_fin, hist = SI_NashSolver(mam, max_iter=2, K=K).solve(list(X_refs), list(U_refs), sigma_ref=16.0, show_progress=False)
+    assert len(hist) >= 1 and all(np.isfinite(h) for h in hist)
+    for (a, b), Xf, Uf in zip(ends, X_fin, U_fin):
+        np.testing.assert_allclose(Xf[:, 0], a, atol=1e-9); np.testing.assert_allclose(Xf[:, -1], b, atol=1e-9)
+        assert (np.linalg.norm(Uf, axis=0) <= 1.0 + 1e-8).all()
+    # inter-sample linearisations were refreshed in setup (and, as in the reference, not used as constraints)
+    assert mam.models[0].extra_constraints == [] and isinstance(mam.models[0].inter_samples, list)
+    assert all(abs(s["grad_u"]).sum() == 0 for s in mam.models[0].inter_samples)
