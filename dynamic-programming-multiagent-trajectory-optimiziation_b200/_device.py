@@ -274,3 +274,30 @@ def clearance_samples(model_id, X, U, sigma, obs_c, total_r, resolution=50):
     check(load().scvx_clearance_samples_batched(model_id, n, K, m, int(resolution), ptr(X), ptr(U), ptr(sigma), ptr(obs_c),
                                                 ptr(total_r), ptr(out), stream_ptr()), "scvx_clearance_samples_batched")
     return out
+
+
+def cross_min_dist2(model_id, X_own, X_all):
+    """min over k of the squared position distance between every local agent and every agent: (n_local, n_agents)."""
+    X_own, X_all = _dev(X_own), _dev(X_all)
+    nl, _, K = X_own.shape
+    N = X_all.shape[0]
+    d2 = torch.empty((nl, N), dtype=F64, device=X_own.device)
+    check(load().scvx_cross_min_dist2(model_id, nl, N, K, ptr(X_own), ptr(X_all), ptr(d2), stream_ptr()), "scvx_cross_min_dist2")
+    return d2
+
+
+def linearize_collision_indexed(model_id, X_own, X_all, nbr_idx, d_min, out=None):
+    """Inter-agent half-spaces for per-agent neighbour lists nbr_idx (n_local, n_sel) int32 (-1 = empty):
+    col_a (n_local, n_sel, d, K), col_b (n_local, n_sel, K)."""
+    _, _, d = MODEL_DIMS[model_id]
+    X_own, X_all = _dev(X_own), _dev(X_all)
+    nl, _, K = X_own.shape
+    assert nbr_idx.is_cuda and nbr_idx.dtype == torch.int32 and nbr_idx.shape[0] == nl
+    nbr_idx = nbr_idx.contiguous()
+    n_sel = nbr_idx.shape[1]
+    if out is None:
+        out = (torch.empty((nl, n_sel, d, K), dtype=F64, device=X_own.device), torch.empty((nl, n_sel, K), dtype=F64, device=X_own.device))
+    a, b = out
+    check(load().scvx_linearize_collision_indexed(model_id, nl, n_sel, X_all.shape[0], K, float(d_min), ptr(X_own), ptr(X_all),
+                                                  ptr(nbr_idx), ptr(a), ptr(b), stream_ptr()), "scvx_linearize_collision_indexed")
+    return out

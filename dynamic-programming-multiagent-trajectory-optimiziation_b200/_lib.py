@@ -61,6 +61,8 @@ SIGNATURES = {
     "scvx_integrate_full_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 4 + [_c_dp]),
     "scvx_linearize_obstacles_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 5 + [_c_dp]),
     "scvx_linearize_collision_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 4 + [_c_dp]),
+    "scvx_cross_min_dist2": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 3 + [_c_dp]),
+    "scvx_linearize_collision_indexed": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),
     "scvx_slab_normals_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int] + [_c_dp] * 7 + [_c_dp]),
     "scvx_solve_workspace_bytes": (ctypes.c_ulonglong, [_c_int, _c_int, _c_int, _c_int, _c_int]),
     "scvx_solve_batched": (_c_int, [ctypes.POINTER(SolveArgs), _c_dp]),

@@ -193,7 +193,7 @@ class BatchedADMM:
     """
 
     def __init__(self, models, d_min, K, rho_admm=1.0, max_iter=10, si_variant=False, group=None, device=None,
-                 n_sub=0, ipm_max_iter=0, neighbor_radius=None):
+                 n_sub=0, ipm_max_iter=0, neighbor_radius=None, neighbor_k=None):
         import torch.distributed as dist
         self.dist = dist if (group is not None or (dist.is_available() and dist.is_initialized())) else None
         self.group = group
@@ -203,6 +203,9 @@ class BatchedADMM:
         self.K, self.d_min, self.rho, self.max_iter, self.si_variant = K, float(d_min), float(rho_admm), max_iter, si_variant
         self.n_sub, self.ipm_max_iter = n_sub, ipm_max_iter
         self.neighbor_radius = neighbor_radius
+        # neighbor_k: couple every agent with its k nearest neighbours only (compact tables; needed when N^2 tables do not
+        # fit: 8192 agents x K=200 would need 26 GB per GPU of half-space tables) -- a documented deviation from the reference
+        self.neighbor_k = None if neighbor_k is None else int(min(neighbor_k, max(len(models) - 1, 1)))
         self.per, self.i0, self.i1 = shard_bounds(self.N, self.world, self.rank)
         self.nl = self.i1 - self.i0
         self.all = AgentBatch(models, K, device)                       # tables for shapes / initial Y
@@ -211,13 +214,14 @@ class BatchedADMM:
         dev = b.device
         if self.nl:
             lb = self.local
-            self.ws = _device.SubproblemWorkspace(lb.model_id, self.nl, K, lb.M, self.N, dev)
+            n_slots = self.neighbor_k if self.neighbor_k is not None else self.N
+            self.ws = _device.SubproblemWorkspace(lb.model_id, self.nl, K, lb.M, n_slots, dev)
             self.mats = tuple(torch.empty((self.nl, r, K - 1), dtype=F64, device=dev)
                               for r in (b.n_x * b.n_x, b.n_x * b.n_u, b.n_x * b.n_u, b.n_x, b.n_x))
             self.obs_a = torch.empty((self.nl, lb.M, b.d, K), dtype=F64, device=dev)
             self.obs_b = torch.empty((self.nl, lb.M, K), dtype=F64, device=dev)
-            self.col_a = torch.empty((self.nl, self.N, b.d, K), dtype=F64, device=dev)
-            self.col_b = torch.empty((self.nl, self.N, K), dtype=F64, device=dev)
+            self.col_a = torch.empty((self.nl, n_slots, b.d, K), dtype=F64, device=dev)
+            self.col_b = torch.empty((self.nl, n_slots, K), dtype=F64, device=dev)
         self.launches = 0
 
     def _gather(self, X_local, U_local):
@@ -245,20 +249,41 @@ class BatchedADMM:
                 _device.foh(lb.model_id, X_loc, U_loc, sig, self.n_sub, out=self.mats)
                 if lb.M:
                     _device.linearize_obstacles(lb.model_id, Xr, lb.obs_c, lb.obs_clear, out=(self.obs_a, self.obs_b))
-                # a_ij about (own reference, neighbour's current trajectory); b = d_min + a.Y_j
-                _device.linearize_collision(lb.model_id, Xr, X_all, self.d_min, i0=self.i0, out=(self.col_a, self.col_b))
-                col_b = self.d_min + (self.col_a * Y[None]).sum(dim=2)
-                mask = torch.ones((self.nl, N), dtype=torch.uint8, device=dev)
-                mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
-                if self.neighbor_radius is not None:
-                    # neighbour culling (documented deviation for large N): keep j only if the trajectories come
-                    # within neighbor_radius at some node
-                    dist2 = ((Xr[:, None, :d, :] - X_all[None, :, :d, :]) ** 2).sum(dim=2).min(dim=2).values
-                    mask &= (dist2 <= self.neighbor_radius ** 2).to(torch.uint8)
-                nact = mask.sum(dim=1).to(F64)
-                # sum over ACTIVE neighbours of Y_j and Lambda_j  (all-pairs: total minus own)
-                mY = torch.einsum("ij,jdk->idk", mask.to(F64), Y)
-                mL = torch.einsum("ij,jdk->idk", mask.to(F64), Lam)
+                if self.neighbor_k is None:
+                    # a_ij about (own reference, neighbour's current trajectory); b = d_min + a.Y_j
+                    _device.linearize_collision(lb.model_id, Xr, X_all, self.d_min, i0=self.i0, out=(self.col_a, self.col_b))
+                    col_b = self.d_min + (self.col_a * Y[None]).sum(dim=2)
+                    mask = torch.ones((self.nl, N), dtype=torch.uint8, device=dev)
+                    mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
+                    if self.neighbor_radius is not None:
+                        # neighbour culling (documented deviation for large N): keep j only if the trajectories come
+                        # within neighbor_radius at some node
+                        dist2 = ((Xr[:, None, :d, :] - X_all[None, :, :d, :]) ** 2).sum(dim=2).min(dim=2).values
+                        mask &= (dist2 <= self.neighbor_radius ** 2).to(torch.uint8)
+                    nact = mask.sum(dim=1).to(F64)
+                    # sum over ACTIVE neighbours of Y_j and Lambda_j  (all-pairs: total minus own)
+                    mY = torch.einsum("ij,jdk->idk", mask.to(F64), Y)
+                    mL = torch.einsum("ij,jdk->idk", mask.to(F64), Lam)
+                    yy = torch.einsum("ij,jdk->i", mask.to(F64), Y * Y)
+                    ly = torch.einsum("ij,jdk->i", mask.to(F64), Lam * Y)
+                else:
+                    # k nearest neighbours (minimum distance over the horizon), compact slot tables
+                    d2 = _device.cross_min_dist2(lb.model_id, Xr, X_all)
+                    d2[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = float("inf")
+                    val, idx = torch.topk(d2, self.neighbor_k, dim=1, largest=False)
+                    sel = torch.isfinite(val)
+                    if self.neighbor_radius is not None:
+                        sel &= val <= self.neighbor_radius ** 2
+                    nbr_idx = torch.where(sel, idx, torch.full_like(idx, -1)).to(torch.int32)
+                    _device.linearize_collision_indexed(lb.model_id, Xr, X_all, nbr_idx, self.d_min, out=(self.col_a, self.col_b))
+                    selw = sel.to(F64)[:, :, None, None]
+                    Ysel = Y[idx] * selw; Lsel = Lam[idx] * selw                       # (nl, k, d, K)
+                    col_b = self.d_min + (self.col_a * Ysel).sum(dim=2)
+                    mask = sel.to(torch.uint8).contiguous()
+                    nact = sel.sum(dim=1).to(F64)
+                    mY = Ysel.sum(dim=1); mL = Lsel.sum(dim=1)
+                    yy = (Ysel * Ysel).sum(dim=(1, 2, 3)); ly = (Lsel * Ysel).sum(dim=(1, 2, 3))
+                    self.last_nbr_idx = nbr_idx
                 quad = self.rho * nact
                 lin = mL - self.rho * mY
                 _device.solve_subproblem(self.ws, self.mats, Xr, Ur, sig, tr, lb.x_init, lb.x_final, lb.pos_lo,
@@ -267,8 +292,6 @@ class BatchedADMM:
                                          quad_rho=quad, lin_p=lin, weight_col=WEIGHT_COLLISION_SLACK,
                                          max_iter=self.ipm_max_iter)
                 # constant terms of the augmented Lagrangian so that `objective` matches agent_solver.py:92-95
-                yy = torch.einsum("ij,jdk->i", mask.to(F64), Y * Y)
-                ly = torch.einsum("ij,jdk->i", mask.to(F64), Lam * Y)
                 const = 0.5 * self.rho * yy - ly
                 objs.append((self.ws.objective + const).clone())
                 self.launches += 4 if lb.M else 3

@@ -221,6 +221,74 @@ slab_normals_kernel(int n_local, int i0, int n_agents, int K, int n_x, const dou
   if (bad && degenerate) atomicAdd(degenerate + i, bad);
 }
 
+
+// ---- neighbour culling for large N (a documented DEVIATION from the reference, which couples all pairs) ----------------
+// cross_min_dist2_kernel: one warp per (local agent i, agent j): min over k of || p_ik - q_jk ||^2 on the position rows.
+// linearize_collision_indexed_kernel: the half-spaces of multi_agent_model.py:61-79 for a per-agent LIST of neighbours
+// (nbr_idx [n_local][n_sel], -1 = empty slot): compact tables [n_local][n_sel][d][K] instead of [n_local][N][d][K].
+template <int D>
+__global__ void __launch_bounds__(128)
+cross_min_dist2_kernel(int n_local, int n_agents, int K, int n_x, const double* __restrict__ X_own,
+                       const double* __restrict__ X_all, double* __restrict__ d2) {
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)n_local * n_agents) return;
+  const int i = (int)(w / n_agents), j = (int)(w - (long long)i * n_agents);
+  const double* Xi = X_own + (size_t)i * n_x * K;
+  const double* Xj = X_all + (size_t)j * n_x * K;
+  double m = INFINITY;
+  for (int k = lane; k < K; k += 32) {
+    double s = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) { const double d = Xi[(size_t)c * K + k] - Xj[(size_t)c * K + k]; s += d * d; }
+    m = fmin(m, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) d2[w] = m;
+}
+
+template <int D>
+__global__ void __launch_bounds__(128)
+linearize_collision_indexed_kernel(int n_local, int n_sel, int K, int n_x, double d_min, const double* __restrict__ X_own,
+                                   const double* __restrict__ X_all, const int* __restrict__ nbr_idx,
+                                   double* __restrict__ col_a, double* __restrict__ col_b) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.z;
+  if (k >= K) return;
+  double p[D];
+#pragma unroll
+  for (int c = 0; c < D; ++c) p[c] = X_own[((size_t)i * n_x + c) * K + k];
+  const int q0 = blockIdx.y * 16;
+  const int q1 = min(q0 + 16, n_sel);
+  for (int q = q0; q < q1; ++q) {
+    const size_t slot = (size_t)i * n_sel + q;
+    const int j = nbr_idx[slot];
+    if (j < 0) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) col_a[(slot * D + c) * K + k] = 0.0;
+      col_b[slot * K + k] = 0.0;
+      continue;
+    }
+    double qq[D], diff[D], nrm2 = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      qq[c] = X_all[((size_t)j * n_x + c) * K + k];
+      diff[c] = p[c] - qq[c];
+      nrm2 += diff[c] * diff[c];
+    }
+    const double inv = 1.0 / (sqrt(nrm2) + EPS_NORMAL);
+    double dot = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+      const double a = diff[c] * inv;
+      col_a[(slot * D + c) * K + k] = a;
+      dot += a * qq[c];
+    }
+    col_b[slot * K + k] = d_min + dot;
+  }
+}
+
 }  // namespace scvx
 
 using namespace scvx;
@@ -284,6 +352,41 @@ extern "C" int scvx_slab_normals_batched(int model_id, int n_local, int i0, int 
   else
     slab_normals_kernel<3><<<grid, 128, 0, st>>>(n_local, i0, n_agents, K, nx, radius, P_own, X_dir, X_off, col_a, col_b, degenerate);
   SCVX_CHECK_LAUNCH("scvx_slab_normals_batched");
+  return SCVX_OK;
+}
+
+extern "C" int scvx_cross_min_dist2(int model_id, int n_local, int n_agents, int K, const double* X_own, const double* X_all,
+                                    double* d2, void* stream) {
+  int nx, nu, d;
+  if (!model_dims(model_id, &nx, &nu, &d)) return bad_arg("model_id");
+  if (n_local < 0 || n_agents < 0 || K < 1) return bad_arg("n_local/n_agents/K");
+  const long long items = (long long)n_local * n_agents;
+  if (items == 0) return SCVX_OK;
+  if (!X_own || !X_all || !d2) return bad_arg("null pointer");
+  const unsigned blocks = (unsigned)((items + 3) / 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d == 2) cross_min_dist2_kernel<2><<<blocks, 128, 0, st>>>(n_local, n_agents, K, nx, X_own, X_all, d2);
+  else cross_min_dist2_kernel<3><<<blocks, 128, 0, st>>>(n_local, n_agents, K, nx, X_own, X_all, d2);
+  SCVX_CHECK_LAUNCH("scvx_cross_min_dist2");
+  return SCVX_OK;
+}
+
+extern "C" int scvx_linearize_collision_indexed(int model_id, int n_local, int n_sel, int n_agents, int K, double d_min,
+                                                const double* X_own, const double* X_all, const int* nbr_idx, double* col_a,
+                                                double* col_b, void* stream) {
+  int nx, nu, d;
+  if (!model_dims(model_id, &nx, &nu, &d)) return bad_arg("model_id");
+  if (n_local < 0 || n_sel < 0 || n_agents < 0 || K < 1) return bad_arg("n_local/n_sel/n_agents/K");
+  if (n_local == 0 || n_sel == 0) return SCVX_OK;
+  if (n_local > 65535) return bad_arg("n_local > 65535 (split the call)");
+  if (!X_own || !X_all || !nbr_idx || !col_a || !col_b) return bad_arg("null pointer");
+  dim3 grid((K + 127) / 128, (n_sel + 15) / 16, n_local);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d == 2)
+    linearize_collision_indexed_kernel<2><<<grid, 128, 0, st>>>(n_local, n_sel, K, nx, d_min, X_own, X_all, nbr_idx, col_a, col_b);
+  else
+    linearize_collision_indexed_kernel<3><<<grid, 128, 0, st>>>(n_local, n_sel, K, nx, d_min, X_own, X_all, nbr_idx, col_a, col_b);
+  SCVX_CHECK_LAUNCH("scvx_linearize_collision_indexed");
   return SCVX_OK;
 }
 

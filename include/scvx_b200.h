@@ -105,6 +105,16 @@ int scvx_linearize_collision_batched(int model_id, int n_local, int i0, int n_ag
                                      const double* X_own, const double* X_nbr,
                                      double* col_a, double* col_b, void* stream);
 
+/* Neighbour culling for large N (a documented DEVIATION from the reference, whose agents couple with ALL others):
+ * scvx_cross_min_dist2: d2 [n_local][n_agents] = min over k of the squared position distance between local agent i
+ * (X_own [n_local][n_x][K]) and agent j (X_all [n_agents][n_x][K]).
+ * scvx_linearize_collision_indexed: the half-spaces of scvx_linearize_collision_batched for a per-agent LIST of neighbours,
+ * nbr_idx [n_local][n_sel] (global agent ids, -1 = empty slot -> zero row): col_a [n_local][n_sel][d][K], col_b [n_local][n_sel][K]. */
+int scvx_cross_min_dist2(int model_id, int n_local, int n_agents, int K, const double* X_own, const double* X_all, double* d2,
+                         void* stream);
+int scvx_linearize_collision_indexed(int model_id, int n_local, int n_sel, int n_agents, int K, double d_min, const double* X_own,
+                                     const double* X_all, const int* nbr_idx, double* col_a, double* col_b, void* stream);
+
 /* Slab rows of the Nash best response: GameUnicycleModel.update_slabs (SCvx/models/game_model.py:56-67) and the rows
  * z_jk.(p_ik - Y_jk) >= collision_radius of get_cost_function (game_model.py:118-124), in the half-space layout of
  * scvx_linearize_collision_batched (a = z, b = radius + z.Y).  z_jk = (P_own_ik - X_dir_jk)/||.|| -- exactly zero when the
