@@ -96,3 +96,27 @@ def test_analysis_metrics_large_vs_oracle():
     assert np.array_equal(dmat.cpu().numpy(), rm) and float(dmin.item()) == rd
     assert np.array_equal(omat.cpu().numpy(), om) and float(omin.item()) == od
     assert np.allclose(dmat.cpu().numpy(), dmat.cpu().numpy().T) and not np.diag(dmat.cpu().numpy()).any()
+
+
+def test_empty_batches_and_bad_arguments():
+    """n = 0 is a no-op for every new entry point; argument errors come back as SCVX_E_BADARG with a message."""
+    import ctypes
+    import torch
+    from scvx_b200 import _device, _lib
+    dev = torch.device("cuda")
+    z = lambda *s: torch.empty(s, dtype=torch.float64, device=dev)   # noqa: E731
+    X0, U0, st = _device.warm_start(_lib.MODEL_UNICYCLE, z(0, 3), z(0, 3), None, None, 0.3, 20)
+    assert X0.shape == (0, 3, 20) and U0.shape == (0, 2, 20) and st.numel() == 0
+    dmin, dmat = _device.min_inter_agent_distance(z(1, 3, 7).zero_())          # one agent: no pair, +inf minimum
+    assert dmat.shape == (1, 1) and np.isinf(dmin.item())
+    nr, ts, h0, gx = _device.intersample(_lib.MODEL_UNICYCLE, z(0, 3, 9), z(0, 2, 9), z(0), z(0, 2, 2), z(0, 2))
+    assert nr.shape == (0, 8, 2)
+    lib = _lib.load()
+    assert lib.scvx_warm_start_batched(99, 1, 20, 0, None, None, None, None, None, 0.0, None, None, None, None) == -1
+    assert b"null pointer" in lib.scvx_last_error() or b"model_id" in lib.scvx_last_error()
+    assert lib.scvx_min_inter_agent_distance(2, 5, 3, 4, None, None, None, None) == -1      # n_rows > n_x
+    assert lib.scvx_intersample_batched(0, 1, 5, 1, 2, None, None, None, None, None, 1.0, 1, 1e-4, 1e-6, 4, None, None, None,
+                                        None, None) == -1                                     # num_samples < 2
+    with pytest.raises(ValueError):                                                          # all distances zero -> no positive entry
+        from scvx_b200.utils.analysis import min_inter_agent_distance
+        min_inter_agent_distance([np.zeros((3, 4)), np.zeros((3, 4))])
