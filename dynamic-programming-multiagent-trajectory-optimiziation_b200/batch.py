@@ -309,7 +309,8 @@ class BatchedADMM:
                 "objective": torch.stack(objs) if objs else None, "mask": mask}
 
 
-SLAB_PENALTY = 1e8               # exact-penalty weight of the hard slab rows (optimization/agent_best_response.py)
+SLAB_PENALTIES = (1e7, 1e8)      # exact-penalty weights of the hard slab rows, escalated while a slack remains
+SLAB_PENALTY = SLAB_PENALTIES[0]  # (see optimization/agent_best_response.py)
 SLAB_TOL = 1e-7
 
 
@@ -321,7 +322,7 @@ class BatchedNash:
     """
 
     def __init__(self, models, K, max_iter=20, tol=1e-3, max_acs_iters=5, acs_tol=1e-3, group=None, device=None,
-                 n_sub=0, ipm_max_iter=0):
+                 n_sub=0, ipm_max_iter=0, neighbor_radius=None, n_colors=1):
         import torch.distributed as dist
         from .optimization.agent_best_response import game_tables
         self.dist = dist if (group is not None or (dist.is_available() and dist.is_initialized())) else None
@@ -331,6 +332,11 @@ class BatchedNash:
         self.N, self.K = len(models), K
         self.max_iter, self.tol, self.max_acs_iters, self.acs_tol = max_iter, tol, max_acs_iters, acs_tol
         self.n_sub, self.ipm_max_iter = n_sub, ipm_max_iter
+        # neighbor_radius: keep the slab rows of neighbour j only if the two trajectories come within this distance at some
+        # knot of the sweep's reference (a documented deviation: the reference keeps all N-1 neighbours; with hundreds of far,
+        # inactive penalty rows per stage the interior-point method needs several times the iterations)
+        self.neighbor_radius = neighbor_radius
+        self.n_colors = max(1, int(n_colors))
         self.per, self.i0, self.i1 = shard_bounds(self.N, self.world, self.rank)
         self.nl = self.i1 - self.i0
         self.all = AgentBatch(models, K, device)
@@ -351,6 +357,7 @@ class BatchedNash:
             self.col_b = torch.empty((self.nl, self.N, K), dtype=F64, device=dev)
             self.mask = torch.ones((self.nl, self.N), dtype=torch.uint8, device=dev)
             self.mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
+            self.self_mask = self.mask.clone()
         self.launches = 0
 
     def _cost_tables(self, X_prev_local):
@@ -364,67 +371,97 @@ class BatchedNash:
         up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(b.device)   # noqa: E731
         return up(np.stack(qd)), up(np.stack(lw)), up(np.stack(qp)), up(np.array(cst))
 
+    def _best_responses(self, X_all, U_all, X_prev_all, sig, tr):
+        """Best responses (with the ACS loop) of ALL local agents against the trajectories X_all; the initial slab normals point
+        along the sweep-start snapshot X_prev_all (agent_best_response.py:66-72).  Returns X_new, U_new, delta, acs, bad, cap, obj."""
+        b, lb = self.all, self.local
+        dev, N = b.device, self.N
+        X_loc = X_all[self.i0:self.i1].contiguous(); U_loc = U_all[self.i0:self.i1].contiguous()
+        _device.foh(lb.model_id, X_loc, U_loc, sig, self.n_sub, out=self.mats)
+        if lb.M:
+            _device.linearize_obstacles(lb.model_id, X_loc, lb.obs_c, lb.obs_clear, out=(self.obs_a, self.obs_b))
+        qd, lw, qp, cst = self._cost_tables(X_loc)
+        if self.neighbor_radius is not None:
+            d2 = _device.cross_min_dist2(lb.model_id, X_loc, X_all)
+            self.mask = self.self_mask & (d2 <= self.neighbor_radius ** 2).to(torch.uint8)
+        _, _, deg = _device.slab_normals(lb.model_id, X_loc, X_prev_all, X_all, self.radius, i0=self.i0, out=(self.col_a, self.col_b))
+        X_new = X_loc.clone(); U_new = U_loc.clone()
+        done = torch.zeros(self.nl, dtype=torch.bool, device=dev)
+        acs = torch.zeros(self.nl, dtype=torch.int32, device=dev)
+        bad = deg > 0
+        not_conv = torch.zeros(self.nl, dtype=torch.bool, device=dev)
+        obj = torch.zeros(self.nl, dtype=F64, device=dev)
+        for _a in range(self.max_acs_iters):
+            live = ~done
+            todo = live.clone()                       # agents still waiting for a slack-free solve
+            for penalty in ((SLAB_PENALTY,) + tuple(p for p in SLAB_PENALTIES if p > SLAB_PENALTY)):
+                _device.solve_subproblem(self.ws, self.mats, X_loc, U_loc, sig, tr, lb.x_init, lb.x_final, lb.pos_lo,
+                                         lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU, WEIGHT_SLACK,
+                                         WEIGHT_SIGMA, col_a=self.col_a, col_b=self.col_b, col_mask=self.mask,
+                                         weight_col=penalty, max_iter=self.ipm_max_iter, quad_diag=qd, lin_w=lw,
+                                         quad_pair=qp, fix_sigma=True)
+                self.launches += 1
+                X_new[todo] = self.ws.X[todo]; U_new[todo] = self.ws.U[todo]
+                obj[todo] = self.ws.objective[todo] + cst[todo]
+                slack = (self.ws.col_slack * self.mask[:, :, None]).amax(dim=(1, 2)) if N > 1 else torch.zeros(self.nl, device=dev, dtype=F64)
+                failed = todo & ((slack > SLAB_TOL) | (self.ws.status == 2))
+                not_conv |= todo & (self.ws.status == 1)
+                todo = failed
+                if not bool(todo.any().item()):
+                    break
+            bad |= todo                               # still a residual slack at the largest weight: infeasible slabs
+            acs += live.to(torch.int32)
+            # dual update: normals along (new own position) - (neighbours' current positions)
+            _, _, deg = _device.slab_normals(lb.model_id, X_new, X_all, X_all, self.radius, i0=self.i0, out=(self.col_a, self.col_b))
+            bad |= deg > 0
+            done |= torch.linalg.norm((X_new - X_loc).reshape(self.nl, -1), dim=1) < self.acs_tol
+            if bool(done.all().item()):
+                break
+        delta = torch.linalg.norm((X_new - X_loc).reshape(self.nl, -1), dim=1)
+        return X_new, U_new, delta, acs, bad, not_conv, obj
+
     def solve(self, X_refs, U_refs, sigma_ref=1.0):
         """X_refs (N, n_x, K), U_refs (N, n_u, K) device tensors on every rank.  Returns dict(X, U, change_hist,
         acs_iters (sweeps, nl), infeasible (sweeps, nl): residual slab slack or vanished normal -- the cases in which the
-        reference raises)."""
+        reference raises; iteration_cap (sweeps, nl): a solve stopped at the interior-point iteration cap).
+        With n_colors > 1 a sweep is split into colour phases (agent index mod n_colors): the agents of a phase respond to the
+        ALREADY UPDATED trajectories of the earlier phases, one all-gather per phase -- Gauss-Seidel between colours."""
         b = self.all
         dev, K, N = b.device, self.K, self.N
         X_all = _device._dev(X_refs).clone(); U_all = _device._dev(U_refs).clone()
         sig = torch.full((max(self.nl, 1),), float(sigma_ref), dtype=F64, device=dev)[:self.nl]
         tr = torch.full((max(self.nl, 1),), float(TRUST_RADIUS0), dtype=F64, device=dev)[:self.nl]
-        change_hist, acs_hist, bad_hist, obj_hist = [], [], [], []
+        change_hist, acs_hist, bad_hist, obj_hist, cap_hist = [], [], [], [], []
+        colour = (torch.arange(self.i0, self.i1, device=dev) % self.n_colors) if self.nl else None
         for _ in range(self.max_iter):
+            X_prev_all = X_all.clone()
+            mx = torch.zeros((), dtype=F64, device=dev)
+            acs_s = bad_s = cap_s = obj_s = None
+            for c in range(self.n_colors):
+                if self.nl:
+                    X_new, U_new, delta, acs, bad, cap, obj = self._best_responses(X_all, U_all, X_prev_all, sig, tr)
+                    take = colour == c
+                    keep = ~take
+                    X_new[keep] = X_all[self.i0:self.i1][keep]; U_new[keep] = U_all[self.i0:self.i1][keep]
+                    if bool(take.any().item()):
+                        mx = torch.maximum(mx, delta[take].max())
+                    if acs_s is None:
+                        acs_s, bad_s, cap_s, obj_s = torch.zeros_like(acs), torch.zeros_like(bad), torch.zeros_like(cap), torch.zeros_like(obj)
+                    acs_s[take] = acs[take]; bad_s[take] = bad[take]; cap_s[take] = cap[take]; obj_s[take] = obj[take]
+                else:
+                    X_new = torch.empty((0, b.n_x, K), dtype=F64, device=dev); U_new = torch.empty((0, b.n_u, K), dtype=F64, device=dev)
+                X_all, U_all = allgather_shards(X_new, U_new, N, self.per, self.dist, self.group)
+                X_all, U_all = X_all.clone(), U_all.clone()
             if self.nl:
-                lb = self.local
-                X_loc = X_all[self.i0:self.i1].contiguous(); U_loc = U_all[self.i0:self.i1].contiguous()
-                _device.foh(lb.model_id, X_loc, U_loc, sig, self.n_sub, out=self.mats)
-                if lb.M:
-                    _device.linearize_obstacles(lb.model_id, X_loc, lb.obs_c, lb.obs_clear, out=(self.obs_a, self.obs_b))
-                qd, lw, qp, cst = self._cost_tables(X_loc)
-                # normals along X_prev -> neighbour_prev (agent_best_response.py:66-72); offsets use the neighbours' positions
-                _, _, deg = _device.slab_normals(lb.model_id, X_loc, X_all, X_all, self.radius, i0=self.i0,
-                                                 out=(self.col_a, self.col_b))
-                X_new = X_loc.clone(); U_new = U_loc.clone()
-                done = torch.zeros(self.nl, dtype=torch.bool, device=dev)
-                acs = torch.zeros(self.nl, dtype=torch.int32, device=dev)
-                bad = deg > 0
-                obj = torch.zeros(self.nl, dtype=F64, device=dev)
-                for _a in range(self.max_acs_iters):
-                    _device.solve_subproblem(self.ws, self.mats, X_loc, U_loc, sig, tr, lb.x_init, lb.x_final, lb.pos_lo,
-                                             lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU, WEIGHT_SLACK,
-                                             WEIGHT_SIGMA, col_a=self.col_a, col_b=self.col_b, col_mask=self.mask,
-                                             weight_col=SLAB_PENALTY, max_iter=self.ipm_max_iter, quad_diag=qd, lin_w=lw,
-                                             quad_pair=qp, fix_sigma=True)
-                    self.launches += 1
-                    live = ~done
-                    X_new[live] = self.ws.X[live]; U_new[live] = self.ws.U[live]
-                    obj[live] = self.ws.objective[live] + cst[live]
-                    slack = (self.ws.col_slack * self.mask[:, :, None]).amax(dim=(1, 2)) if N > 1 else torch.zeros(self.nl, device=dev, dtype=F64)
-                    bad |= live & ((slack > SLAB_TOL) | (self.ws.status == 2))
-                    acs += live.to(torch.int32)
-                    # dual update: normals along (new own position) - (neighbours' current positions)
-                    _, _, deg = _device.slab_normals(lb.model_id, X_new, X_all, X_all, self.radius, i0=self.i0,
-                                                     out=(self.col_a, self.col_b))
-                    bad |= deg > 0
-                    done |= torch.linalg.norm((X_new - X_loc).reshape(self.nl, -1), dim=1) < self.acs_tol
-                    if bool(done.all().item()):
-                        break
-                delta = torch.linalg.norm((X_new - X_loc).reshape(self.nl, -1), dim=1)
-                acs_hist.append(acs); bad_hist.append(bad.clone()); obj_hist.append(obj)
-            else:
-                X_new = torch.empty((0, b.n_x, K), dtype=F64, device=dev); U_new = torch.empty((0, b.n_u, K), dtype=F64, device=dev)
-                delta = torch.zeros(0, dtype=F64, device=dev)
-            mx = delta.max() if self.nl else torch.zeros((), dtype=F64, device=dev)
+                acs_hist.append(acs_s); bad_hist.append(bad_s); obj_hist.append(obj_s); cap_hist.append(cap_s)
             if self.dist and self.world > 1:
                 mx = mx.clone()
                 self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX, group=self.group)
-            X_all, U_all = allgather_shards(X_new, U_new, N, self.per, self.dist, self.group)
-            X_all, U_all = X_all.clone(), U_all.clone()
             change_hist.append(float(mx.item()))
             if change_hist[-1] < self.tol:
                 break
         return {"X": X_all, "U": U_all, "change_hist": change_hist,
                 "acs_iters": torch.stack(acs_hist) if acs_hist else None,
                 "infeasible": torch.stack(bad_hist) if bad_hist else None,
-                "objective": torch.stack(obj_hist) if obj_hist else None}
+                "objective": torch.stack(obj_hist) if obj_hist else None,
+                "iteration_cap": torch.stack(cap_hist) if cap_hist else None}

@@ -2,7 +2,7 @@
 
 Sub-problem = SCProblem + the GameUnicycleModel cost + slab rows z_jk.(p_ik - Y_jk) >= collision_radius + sigma == sigma_ref.
 On the device the cost becomes the kernel's quadratic tables, sigma is frozen, and the HARD slab rows are carried as hinge
-rows with an exact penalty (weight SLAB_PENALTY >> any optimal multiplier): when the hard-constrained problem is feasible
+rows with an exact penalty (weights SLAB_PENALTIES, escalated only while a slab slack remains): when the hard-constrained problem is feasible
 the minimisers coincide and every slab slack is zero; when it is not -- the reference's ECOS reports infeasibility -- the
 residual slack is detected and RuntimeError is raised, as the reference does.
 """
@@ -15,7 +15,12 @@ from ..discretization.first_order_hold import FirstOrderHold
 from ..global_parameters import TRUST_RADIUS0, WEIGHT_NU, WEIGHT_SIGMA, WEIGHT_SLACK, K
 from .sc_problem import SCProblem, _Holder
 
-SLAB_PENALTY = 1e8          # exact-penalty weight of the hard slab rows: must dominate WEIGHT_SLACK (soft obstacle rows)
+# Exact-penalty weights of the hard slab rows, tried in order until every slab slack vanishes.  The weight must dominate
+# WEIGHT_SLACK = 1e6 of the SOFT obstacle rows (at 1e6 a slab that conflicts with an obstacle keeps a residual slack); 1e7
+# converges like the plain problem (tools/robustness_scan_game.py: 128 agents x 127 slots, 17 IPM iterations, all optimal),
+# 1e8 is exact in tighter conflicts but needs 2-4x the iterations, so it is only the fall-back.
+SLAB_PENALTIES = (1e7, 1e8)
+SLAB_PENALTY = SLAB_PENALTIES[0]
 SLAB_TOL = 1e-7             # a larger residual slack means the hard rows are infeasible
 
 
@@ -88,12 +93,15 @@ class AgentBestResponse:
             col_a = up(z).unsqueeze(0)
             col_b = up(self.model.collision_radius + (z * Y).sum(axis=1)).unsqueeze(0)
         qd, lw, qp, const = game_tables(self.model, self.X_prev_param.value, K)
-        ws = self.scp._solve_device(max_iter=int(solver_kwargs.get("max_iter", 0)), col_a=col_a, col_b=col_b,
-                                    weight_col=SLAB_PENALTY, quad_diag=up(qd).unsqueeze(0), lin_w=up(lw).unsqueeze(0),
-                                    quad_pair=up(qp).unsqueeze(0), fix_sigma=True)
-        if self.scp.status == 2:
-            raise RuntimeError("SCProblem error inside AgentBestResponse")
-        if js and float(ws.col_slack[0].max().item()) > SLAB_TOL:
+        for penalty in (SLAB_PENALTIES if js else SLAB_PENALTIES[:1]):
+            ws = self.scp._solve_device(max_iter=int(solver_kwargs.get("max_iter", 0)), col_a=col_a, col_b=col_b,
+                                        weight_col=penalty, quad_diag=up(qd).unsqueeze(0), lin_w=up(lw).unsqueeze(0),
+                                        quad_pair=up(qp).unsqueeze(0), fix_sigma=True)
+            if self.scp.status == 2:
+                raise RuntimeError("SCProblem error inside AgentBestResponse")
+            if not js or float(ws.col_slack[0].max().item()) <= SLAB_TOL:
+                break
+        else:
             raise RuntimeError("SCProblem error inside AgentBestResponse")      # hard slab rows infeasible
         self.scp.prob.value += const
         X_i = self.scp.get_variable("X")

@@ -230,3 +230,30 @@ def test_si_best_response_vs_bracket_and_si_nash_mirror(cuda):
     # inter-sample linearisations were refreshed in setup (and, as in the reference, not used as constraints)
     assert mam.models[0].extra_constraints == [] and isinstance(mam.models[0].inter_samples, list)
     assert all(abs(s["grad_u"]).sum() == 0 for s in mam.models[0].inter_samples)
+
+
+def test_batched_nash_colour_phases_are_gauss_seidel_between_colours(cuda):
+    """Two colours (agent index mod 2): the odd agents respond to the even agents' UPDATED trajectories, so the slab rows of the
+    last responder hold against what its partner actually flies -- every crossing pair ends at >= its collision radius.
+    (In one Jacobi phase both partners move at once and the guarantee is lost.)"""
+    from scvx_b200.batch import BatchedNash
+    from scvx_b200.models.game_model import GameUnicycleModel
+    K, pairs = 40, 6
+    rng = np.random.default_rng(3)
+    s = np.linspace(0, 1, K)
+    models, Xr = [], np.zeros((2 * pairs, 3, K))
+    for q in range(pairs):
+        ox, w, hgt = 6.0 * q, rng.uniform(1.5, 2.5), rng.uniform(3.5, 4.5)
+        for h, (x0, x1) in enumerate(((0.0, w), (w, 0.0))):
+            i = 2 * q + h
+            r0 = np.array([ox + x0, -1.0, 0.0]); r1 = np.array([ox + x1, hgt - 1.0, 0.0])
+            models.append(GameUnicycleModel(r_init=r0, r_final=r1, obstacles=[], control_weight=5.0, collision_radius=0.3,
+                                            control_rate_weight=5.0, curvature_weight=100.0, bounds=(-5.0, 6.0 * pairs + 5.0), robot_radius=0.1))
+            Xr[i, 0] = r0[0] + (r1[0] - r0[0]) * s + (0.5 * np.sin(np.pi * s) if h else 0.0)
+            Xr[i, 1] = r0[1] + (r1[1] - r0[1]) * s
+    out = BatchedNash(models, K, max_iter=3, neighbor_radius=3.0, n_colors=2).solve(helpers.to_dev(Xr, cuda),
+                                                                                  helpers.to_dev(np.zeros((2 * pairs, 2, K)), cuda), 8.0)
+    X = out["X"].cpu().numpy()
+    assert not out["infeasible"].any()
+    sep = [np.linalg.norm(X[2 * q, :2] - X[2 * q + 1, :2], axis=0).min() for q in range(pairs)]
+    assert min(sep) >= 0.3 - 1e-6, sep
