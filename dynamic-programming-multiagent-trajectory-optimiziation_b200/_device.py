@@ -138,7 +138,8 @@ class SubproblemWorkspace:
 def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_radius, x_init, x_final, pos_lo,
                      pos_hi, v_max, w_max, obs_a, obs_b, weight_nu, weight_slack, weight_sigma,
                      col_a=None, col_b=None, col_mask=None, quad_rho=None, lin_p=None, weight_col=1e5,
-                     max_iter=0, norm1_induced=True, quad_diag=None, lin_w=None, quad_pair=None, fix_sigma=False):
+                     max_iter=0, norm1_induced=True, quad_diag=None, lin_w=None, quad_pair=None, fix_sigma=False,
+                     block_order=None):
     """SCProblem.solve / AgentSolver.solve for a batch (sc_problem.py:15-105, agent_solver.py:43-117).
     Results land in the workspace's output tensors."""
     a = SolveArgs()
@@ -161,6 +162,7 @@ def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_
     a.col_a, a.col_b, a.col_mask = P(col_a), P(col_b), P(col_mask)
     a.quad_rho, a.lin_p = P(quad_rho), P(lin_p)
     a.quad_diag, a.lin_w, a.quad_pair, a.fix_sigma = P(quad_diag), P(lin_w), P(quad_pair), 1 if fix_sigma else 0
+    a.block_order = P(block_order)
     a.weight_nu, a.weight_slack, a.weight_sigma, a.weight_col = float(weight_nu), float(weight_slack), float(weight_sigma), float(weight_col)
     a.X, a.U, a.nu, a.sigma = ptr(ws.X), ptr(ws.U), ptr(ws.nu), ptr(ws.sigma)
     a.s_prime = ptr(ws.s_prime) if ws.M else None
@@ -300,4 +302,14 @@ def linearize_collision_indexed(model_id, X_own, X_all, nbr_idx, d_min, out=None
     a, b = out
     check(load().scvx_linearize_collision_indexed(model_id, nl, n_sel, X_all.shape[0], K, float(d_min), ptr(X_own), ptr(X_all),
                                                   ptr(nbr_idx), ptr(a), ptr(b), stream_ptr()), "scvx_linearize_collision_indexed")
+    return out
+
+
+def order_by_iters(iters, out=None):
+    """Longest-first launch order from a solve's iteration counts (int32 (n,) -> int32 (n,) permutation)."""
+    assert iters.is_cuda and iters.dtype == torch.int32
+    iters = iters.contiguous()
+    if out is None:
+        out = torch.empty_like(iters)
+    check(load().scvx_order_by_iters(iters.numel(), ptr(iters), ptr(out), stream_ptr()), "scvx_order_by_iters")
     return out

@@ -78,9 +78,12 @@ class BatchedSCvx:
         self.obs_a = torch.empty((n, b.M, b.d, K), dtype=F64, device=dev)
         self.obs_b = torch.empty((n, b.M, K), dtype=F64, device=dev)
         self.launches = 0
+        self._order = None            # longest-first block order from the previous iteration's IPM iteration counts
+        self._order_buf = torch.empty(n, dtype=torch.int32, device=dev)
 
     def iterate(self, X, U, sigma, tr, active, metrics_row, solver_events=None):
-        """One outer iteration, in place on (X, U, sigma, tr, active): 4 kernel launches.
+        """One outer iteration, in place on (X, U, sigma, tr, active): 5 kernel launches (FOH, obstacle linearisation, sub-problem,
+        bookkeeping, and the longest-first block order for the NEXT iteration's sub-problem launch).
         solver_events = (start, end) CUDA events recorded around the sub-problem kernel on the launching stream."""
         b = self.batch
         _device.foh(b.model_id, X, U, sigma, self.n_sub, out=self.mats)
@@ -90,12 +93,13 @@ class BatchedSCvx:
             solver_events[0].record(torch.cuda.current_stream())
         _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
                                  b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
-                                 self.weight_sigma, max_iter=self.ipm_max_iter)
+                                 self.weight_sigma, max_iter=self.ipm_max_iter, block_order=self._order)
         if solver_events is not None:
             solver_events[1].record(torch.cuda.current_stream())
+        self._order = _device.order_by_iters(self.ws.iters, out=self._order_buf)
         _device.outer_update(b.model_id, b.M, self.conv_tol, self.ws.X, self.ws.U, self.ws.nu, self.ws.sigma,
                              self.ws.s_prime, X, U, sigma, tr, active, metrics_row)
-        self.launches += 4 if b.M else 3
+        self.launches += 5 if b.M else 4
 
     # -- host-buffer API: the call a user holding numpy arrays makes ---------------------------------------------
     def make_host_buffers(self):
@@ -241,6 +245,7 @@ class BatchedADMM:
         tr = torch.full((max(self.nl, 1),), float(TRUST_RADIUS0), dtype=F64, device=dev)[:self.nl]
         primal_hist, dual_hist, objs = [], [], []
         mask = None
+        order = None
         for _ in range(self.max_iter):
             if self.nl:
                 lb = self.local
@@ -290,7 +295,8 @@ class BatchedADMM:
                                          lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU,
                                          WEIGHT_SLACK, WEIGHT_SIGMA, col_a=self.col_a, col_b=col_b, col_mask=mask,
                                          quad_rho=quad, lin_p=lin, weight_col=WEIGHT_COLLISION_SLACK,
-                                         max_iter=self.ipm_max_iter)
+                                         max_iter=self.ipm_max_iter, block_order=order)
+                order = _device.order_by_iters(self.ws.iters)          # longest-first launch order for the next round
                 # constant terms of the augmented Lagrangian so that `objective` matches agent_solver.py:92-95
                 const = 0.5 * self.rho * yy - ly
                 objs.append((self.ws.objective + const).clone())
@@ -359,6 +365,7 @@ class BatchedNash:
             self.mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
             self.self_mask = self.mask.clone()
         self.launches = 0
+        self._order = None
 
     def _cost_tables(self, X_prev_local):
         """quad_diag (nl, ns), lin_w (nl, ns, K), quad_pair (nl, ns), const (nl,) of the local agents."""
@@ -399,7 +406,8 @@ class BatchedNash:
                                          lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU, WEIGHT_SLACK,
                                          WEIGHT_SIGMA, col_a=self.col_a, col_b=self.col_b, col_mask=self.mask,
                                          weight_col=penalty, max_iter=self.ipm_max_iter, quad_diag=qd, lin_w=lw,
-                                         quad_pair=qp, fix_sigma=True)
+                                         quad_pair=qp, fix_sigma=True, block_order=self._order)
+                self._order = _device.order_by_iters(self.ws.iters)
                 self.launches += 1
                 X_new[todo] = self.ws.X[todo]; U_new[todo] = self.ws.U[todo]
                 obj[todo] = self.ws.objective[todo] + cst[todo]

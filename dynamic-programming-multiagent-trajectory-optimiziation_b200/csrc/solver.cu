@@ -568,7 +568,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
   constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
   constexpr int NSP = Dm::NSP, SD = Dm::SD, SR = Dm::SR, NJ = Dm::NJ, STG = Dm::STG, NPLAIN = Dm::NPLAIN;
   constexpr bool BALL = Dm::BALL;
-  const int K = a.K, agent = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int K = a.K, agent = a.block_order ? a.block_order[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const int Mobs = a.M, NH = a.M + a.n_nbr;
 
   extern __shared__ __align__(16) double smem[];
@@ -1824,6 +1824,28 @@ extern "C" int scvx_debug_phase_cycles(unsigned long long* out32, int reset) {
   (void)reset;
   return SCVX_OK;
 #endif
+}
+
+// rank of agent i in the longest-first order = #{j : iters_j > iters_i} + #{j < i : iters_j == iters_i}; order[rank] = i.
+__global__ void __launch_bounds__(256) order_by_iters_kernel(int n, const int* __restrict__ iters, int* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int mine = iters[i];
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const int v = iters[j];
+    rank += (v > mine || (v == mine && j < i)) ? 1 : 0;
+  }
+  order[rank] = i;
+}
+
+extern "C" int scvx_order_by_iters(int n_agents, const int* iters, int* order, void* stream) {
+  if (n_agents < 0) return bad_arg("n_agents");
+  if (n_agents == 0) return SCVX_OK;
+  if (!iters || !order) return bad_arg("null pointer");
+  order_by_iters_kernel<<<(n_agents + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_agents, iters, order);
+  SCVX_CHECK_LAUNCH("scvx_order_by_iters");
+  return SCVX_OK;
 }
 
 extern "C" unsigned long long scvx_solve_workspace_bytes(int model_id, int n_agents, int K, int M, int n_nbr) {

@@ -178,8 +178,14 @@ typedef struct scvx_solve_args {
   const double *lin_w;                            /* [n][n_x+n_u][K] or NULL */
   const double *quad_pair;                        /* [n][n_x+n_u] or NULL */
   int fix_sigma;
+  /* Launch order of the agents' thread blocks: block b solves agent block_order[b] (a permutation of 0..n-1), NULL = identity.
+   * Agents differ 4x in interior-point iterations; starting the long ones first (scvx_order_by_iters on the previous outer
+   * iteration's counts) removes most of the idle tail of the launch.  Results do not depend on the order. */
+  const int *block_order;
 } scvx_solve_args;
 
+/* order[r] = index of the agent with the r-th LARGEST iters (ties by index): a longest-first launch order for the next solve */
+int scvx_order_by_iters(int n_agents, const int* iters, int* order, void* stream);
 /* bytes of device workspace scvx_solve_batched needs for these sizes */
 unsigned long long scvx_solve_workspace_bytes(int model_id, int n_agents, int K, int M, int n_nbr);
 int scvx_solve_batched(const scvx_solve_args* args, void* stream);
