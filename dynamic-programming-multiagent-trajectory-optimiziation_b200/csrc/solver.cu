@@ -22,7 +22,11 @@
 // whole factor resident in shared memory; reductions use warp shuffles.  Row state (s, lambda) lives in a global
 // workspace laid out [row][k] so that every access is coalesced over k.
 // (The first version walked the stages sequentially on warp 0: profiles/r01a shows it latency-bound with 3 of 4
-// warps parked at a barrier; cyclic reduction removes the O(K) dependent chain.)
+// warps parked at a barrier; cyclic reduction removes the O(K) dependent chain.  profiles/r01g: the four step passes are
+// compile-time instantiations, reciprocals are branch-free, hinge rows are fetched four at a time, and the blocks of a launch
+// run longest-first -- scvx_solve_args.block_order.)
+// Best-response (Nash game) terms: diagonal / linear / consecutive-difference quadratics and sigma == sigma_ref, see
+// scvx_solve_args.quad_diag .. fix_sigma in include/scvx_b200.h.
 #include <type_traits>
 #include "common.cuh"
 #include "reduce.cuh"
@@ -201,12 +205,8 @@ struct Scal {
 template <int NS>
 __device__ __forceinline__ void chol_inverse(const double (*Din)[NS], double (*Li)[NS]) {
   double L[NS][NS], dinv[NS];
-  double tr = 0.0;
-#pragma unroll
-  for (int i = 0; i < NS; ++i) tr += Din[i][i];
   // no diagonal regularisation: a relative shift of 1e-13 x trace was measured to floor the dual residual at ~1e-6
   // relative (objective errors up to 2e-6); frozen pivots are the safeguard instead.
-  (void)tr;
 #pragma unroll
   for (int j = 0; j < NS; ++j) {
     const double d0 = Din[j][j];
@@ -553,7 +553,6 @@ __device__ __forceinline__ void schur_solve(const double* Sm, const double* rhs,
 #pragma unroll
   for (int i = 0; i < 4; ++i) out[i] = x[i];
 }
-__device__ __forceinline__ void schur_factor_solve(double* Sm, const double* rhs, double* out) { schur_solve(Sm, rhs, out); }
 
 // coefficients of the three global rows  t_x + t_u +- (sigma - sigma_ref) <= r,  -sigma <= 0  on (sigma, t_nu, t_x, t_u)
 __device__ __forceinline__ constexpr double gG(int r, int i) {
@@ -1295,7 +1294,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
             if (cb < 4) { gl[18 + ca * 4 + cb] -= v; if (cb != ca) gl[18 + cb * 4 + ca] -= v; }
             else gl[34 + ca] -= v;
           }
-        schur_factor_solve(gl + 18, gl + 34, gl + 4);
+        schur_solve(gl + 18, gl + 34, gl + 4);
       }
       __syncthreads();
     }
