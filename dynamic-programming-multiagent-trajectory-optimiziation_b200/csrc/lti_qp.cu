@@ -13,8 +13,9 @@
 // primal/dual step lengths.  The Newton step is an equality-constrained LQ problem: a Riccati recursion handles the
 // dynamics exactly; the terminal equality is enforced through n extra right-hand sides (one per terminal multiplier) and an
 // n x n solve.  The shared slack S_t of a time step is eliminated analytically (rank-one correction of the stage Hessian).
-// One thread block per robot; row passes are parallel over t; the Riccati sweeps are sequential in t (thread 0) -- T is 51
-// or 81 and the blocks are 4x4 / 6x6, a first version that favours being right (SURVEY 8 a14/a15 came last this round).
+// One thread block per robot; row passes are parallel over t; the Riccati sweeps are sequential in t but cooperative within
+// warp 0: every small matrix product (4x4 / 6x6 blocks, N+1 right-hand sides) is one entry per lane between __syncwarp's, and
+// the corrector solve reuses the predictor's matrix recursion and terminal-multiplier columns (only column 0 is redone).
 #include "common.cuh"
 #include "reduce.cuh"
 
@@ -36,6 +37,8 @@ struct LtiDims {
                                + N * N + M * N + M * N + M * M   // P, K, Qux, Quu^-1
                                + M * NR + N * NR                // k, p (all right-hand sides)
                                + N + M;                         // best primal-feasible iterate seen
+  // scratch of the warp-cooperative Riccati sweeps: PA, PB, Quu, pc, qu, qx, xs (two buffers), us, Mt, nu
+  static constexpr int SCR = N * N + N * M + M * M + N * NR + M * NR + N * NR + 2 * N * NR + M * NR + N * N + N;
 };
 
 // row-state layout in the global workspace, per robot: lamT[NE][T], sT[NE][T], lamB[4][T], sB[4][T],
@@ -77,6 +80,16 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
   double* AB = red + 9 * 12;              // A [N*N], B [N*M]
   double* Am = AB;
   double* Bm = AB + N * N;
+  double* sPA = Bm + N * M;               // Riccati scratch (warp 0)
+  double* sPB = sPA + N * N;
+  double* sQuu = sPB + N * M;
+  double* sPc = sQuu + M * M;
+  double* sQu = sPc + N * NR;
+  double* sQv = sQu + M * NR;
+  double* sXs = sQv + N * NR;
+  double* sUs = sXs + 2 * N * NR;
+  double* sMt = sUs + M * NR;
+  double* sNu = sMt + N * N;
 
   const double* x = a.x + (size_t)robot * T * N;
   const double* u = a.u + (size_t)robot * T * M;
@@ -144,136 +157,271 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
   const int max_iter = a.max_iter > 0 ? a.max_iter : 60;
   double obj_prev = 0.0;
 
-  // ---- Riccati LQ solve on thread 0 (matrix part optional) ------------------------------------------------------
+  // ---- Riccati LQ solve on warp 0, lanes spread over the entries of each small matrix product ------------------------
+  // with_matrix = true  (predictor): matrix recursion + all NR right-hand sides (column 0 = the gradient, columns 1..N = the
+  //                      terminal multipliers); the terminal response matrix Mt is kept in shared memory.
+  // with_matrix = false (corrector): P, K, Qux, Quu^-1 and columns 1..N of p / k / Mt are unchanged -- only column 0 is redone.
+  // Each time step is a handful of __syncwarp-separated stages; every stage is one entry (<= N multiply-adds) per lane.
   auto riccati = [&](bool with_matrix, double* out_d, double* out_w) {
-    // backward
-    for (int c = 0; c < NR; ++c)
-      for (int i = 0; i < N; ++i) pp[(size_t)(T - 1) * N * NR + i * NR + c] = (c >= 1 && c - 1 == i) ? 1.0 : 0.0;
-    if (with_matrix)
-      for (int i = 0; i < N * N; ++i) Pm[(size_t)(T - 1) * N * N + i] = 0.0;
+    const int lane = tid;                               // called by tid < 32 only
+    const int nc = with_matrix ? NR : 1;                // right-hand-side columns handled in this call
+    if (with_matrix) {
+      for (int e = lane; e < N * NR; e += 32) { const int i = e / NR, c = e - i * NR; pp[(size_t)(T - 1) * N * NR + e] = (c >= 1 && c - 1 == i) ? 1.0 : 0.0; }
+      for (int e = lane; e < N * N; e += 32) Pm[(size_t)(T - 1) * N * N + e] = 0.0;
+    }
+    __syncwarp();
+    // ---- backward
     for (int t = T - 2; t >= 0; --t) {
       const double* Pn = Pm + (size_t)(t + 1) * N * N;
       double* Pt = Pm + (size_t)t * N * N;
       double* Kt = Km + (size_t)t * M * N;
       double* Qx = Qux + (size_t)t * M * N;
       double* Qi = Qui + (size_t)t * M * M;
-      if (with_matrix) {
-        double PA[N][N], PB[N][M];
-        for (int i = 0; i < N; ++i) {
-          for (int j = 0; j < N; ++j) { double s = 0.0; for (int l = 0; l < N; ++l) s += Pn[i * N + l] * Am[l * N + j]; PA[i][j] = s; }
-          for (int j = 0; j < M; ++j) { double s = 0.0; for (int l = 0; l < N; ++l) s += Pn[i * N + l] * Bm[l * M + j]; PB[i][j] = s; }
-        }
-        double Quu[M][M];
-        for (int i = 0; i < M; ++i)
-          for (int j = 0; j < M; ++j) { double s = Rm[(size_t)t * M * M + i * M + j]; for (int l = 0; l < N; ++l) s += Bm[l * M + i] * PB[l][j]; Quu[i][j] = s; }
-        for (int i = 0; i < M; ++i)
-          for (int j = 0; j < N; ++j) { double s = 0.0; for (int l = 0; l < N; ++l) s += Bm[l * M + i] * PA[l][j]; Qx[i * N + j] = s; }
-        // inverse of the SPD M x M block by Gauss-Jordan (M = 2 or 3)
-        double Ai[M][2 * M];
-        for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) { Ai[i][j] = Quu[i][j]; Ai[i][M + j] = (i == j) ? 1.0 : 0.0; }
-        for (int c = 0; c < M; ++c) {
-          const double r = 1.0 / Ai[c][c];
-          for (int j = 0; j < 2 * M; ++j) Ai[c][j] *= r;
-          for (int i = 0; i < M; ++i) if (i != c) { const double f = Ai[i][c]; for (int j = 0; j < 2 * M; ++j) Ai[i][j] -= f * Ai[c][j]; }
-        }
-        for (int i = 0; i < M; ++i) for (int j = 0; j < M; ++j) Qi[i * M + j] = Ai[i][M + j];
-        for (int i = 0; i < M; ++i)
-          for (int j = 0; j < N; ++j) { double s = 0.0; for (int l = 0; l < M; ++l) s -= Qi[i * M + l] * Qx[l * N + j]; Kt[i * N + j] = s; }
-        // P_t = Q_t + A'PA + Qux'K  (symmetrised)
-        double Pt_[N][N];
-        for (int i = 0; i < N; ++i)
-          for (int j = 0; j < N; ++j) {
-            double s = 0.0;
-            for (int l = 0; l < N; ++l) s += Am[l * N + i] * PA[l][j];
-            for (int l = 0; l < M; ++l) s += Qx[l * N + i] * Kt[l * N + j];
-            if (i < DC && j < DC) s += Qp[(size_t)t * DC * DC + i * DC + j];
-            Pt_[i][j] = s;
-          }
-        for (int i = 0; i < N; ++i) for (int j = 0; j < N; ++j) Pt[i * N + j] = 0.5 * (Pt_[i][j] + Pt_[j][i]);
-      }
-      // vector part, all right-hand sides
       const double* pn = pp + (size_t)(t + 1) * N * NR;
       double* pt = pp + (size_t)t * N * NR;
       double* kt = kk + (size_t)t * M * NR;
-      double pc[N][NR];
-      for (int i = 0; i < N; ++i) {
-        for (int c = 0; c < NR; ++c) pc[i][c] = pn[i * NR + c];
+      // stage a: PA = P A, PB = P B | pc = p_next (+ P c~ in column 0)
+      if (with_matrix) {
+        for (int e = lane; e < N * (N + M); e += 32) {
+          if (e < N * N) {
+            const int i = e / N, j = e - i * N;
+            double s = 0.0;
+#pragma unroll
+            for (int l = 0; l < N; ++l) s += Pn[i * N + l] * Am[l * N + j];
+            sPA[e] = s;
+          } else {
+            const int e2 = e - N * N, i = e2 / M, j = e2 - i * M;
+            double s = 0.0;
+#pragma unroll
+            for (int l = 0; l < N; ++l) s += Pn[i * N + l] * Bm[l * M + j];
+            sPB[e2] = s;
+          }
+        }
+      }
+      for (int e = lane; e < N * nc; e += 32) {
+        const int i = e / nc, c = e - i * nc;
+        double v = pn[i * NR + c];
+        if (c == 0) {
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < N; ++l) s += Pn[i * N + l] * ct[(size_t)t * N + l];
+          v += s;
+        }
+        sPc[i * NR + c] = v;
+      }
+      __syncwarp();
+      // stage b: Quu = R + B'PB, Qux = B'PA | qu = B'pc (+ r), qx = A'pc (+ q)
+      if (with_matrix) {
+        for (int e = lane; e < M * (M + N); e += 32) {
+          if (e < M * M) {
+            const int i = e / M, j = e - i * M;
+            double s = Rm[(size_t)t * M * M + e];
+#pragma unroll
+            for (int l = 0; l < N; ++l) s += Bm[l * M + i] * sPB[l * M + j];
+            sQuu[e] = s;
+          } else {
+            const int e2 = e - M * M, i = e2 / N, j = e2 - i * N;
+            double s = 0.0;
+#pragma unroll
+            for (int l = 0; l < N; ++l) s += Bm[l * M + i] * sPA[l * N + j];
+            Qx[e2] = s;
+          }
+        }
+      }
+      for (int e = lane; e < (M + N) * nc; e += 32) {
+        const int r = e / nc, c = e - r * nc;
+        if (r < M) {
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < N; ++l) s += Bm[l * M + r] * sPc[l * NR + c];
+          sQu[r * NR + c] = s + ((c == 0) ? rv[(size_t)t * M + r] : 0.0);
+        } else {
+          const int i = r - M;
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < N; ++l) s += Am[l * N + i] * sPc[l * NR + c];
+          sQv[i * NR + c] = s + ((c == 0) ? qv[(size_t)t * N + i] : 0.0);
+        }
+      }
+      __syncwarp();
+      if (with_matrix) {
+        // stage c: inverse of the SPD M x M block by Gauss-Jordan (M = 2 or 3), every lane redundantly in registers
+        double Ai[M][2 * M];
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int j = 0; j < M; ++j) { Ai[i][j] = sQuu[i * M + j]; Ai[i][M + j] = (i == j) ? 1.0 : 0.0; }
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+          const double r = 1.0 / Ai[c][c];
+#pragma unroll
+          for (int j = 0; j < 2 * M; ++j) Ai[c][j] *= r;
+#pragma unroll
+          for (int i = 0; i < M; ++i)
+            if (i != c) {
+              const double f = Ai[i][c];
+#pragma unroll
+              for (int j = 0; j < 2 * M; ++j) Ai[i][j] -= f * Ai[c][j];
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int i = 0; i < M; ++i)
+#pragma unroll
+            for (int j = 0; j < M; ++j) Qi[i * M + j] = Ai[i][M + j];
+        }
+        __syncwarp();
+      }
+      // stage d: K = -Quu^-1 Qux | k = -Quu^-1 qu
+      if (with_matrix) {
+        for (int e = lane; e < M * N; e += 32) {
+          const int i = e / N, j = e - i * N;
+          double s = 0.0;
+#pragma unroll
+          for (int l = 0; l < M; ++l) s -= Qi[i * M + l] * Qx[l * N + j];
+          Kt[e] = s;
+        }
+      }
+      for (int e = lane; e < M * nc; e += 32) {
+        const int i = e / nc, c = e - i * nc;
         double s = 0.0;
-        for (int l = 0; l < N; ++l) s += Pn[i * N + l] * ct[(size_t)t * N + l];
-        pc[i][0] += s;
+#pragma unroll
+        for (int l = 0; l < M; ++l) s -= Qi[i * M + l] * sQu[l * NR + c];
+        kt[i * NR + c] = s;
       }
-      double qu[M][NR], qx[N][NR];
-      for (int c = 0; c < NR; ++c) {
-        for (int i = 0; i < M; ++i) { double s = 0.0; for (int l = 0; l < N; ++l) s += Bm[l * M + i] * pc[l][c]; qu[i][c] = s + ((c == 0) ? rv[(size_t)t * M + i] : 0.0); }
-        for (int i = 0; i < N; ++i) { double s = 0.0; for (int l = 0; l < N; ++l) s += Am[l * N + i] * pc[l][c]; qx[i][c] = s + ((c == 0) ? qv[(size_t)t * N + i] : 0.0); }
+      __syncwarp();
+      // stage e: P_t = Q_t + A'PA + Qux'K (symmetrised) | p = qx + Qux'k
+      if (with_matrix) {
+        for (int e = lane; e < N * N; e += 32) {
+          const int i = e / N, j = e - i * N;
+          double s = 0.0, s2 = 0.0;
+#pragma unroll
+          for (int l = 0; l < N; ++l) { s += Am[l * N + i] * sPA[l * N + j]; s2 += Am[l * N + j] * sPA[l * N + i]; }
+#pragma unroll
+          for (int l = 0; l < M; ++l) { s += Qx[l * N + i] * Kt[l * N + j]; s2 += Qx[l * N + j] * Kt[l * N + i]; }
+          if (i < DC && j < DC) { s += Qp[(size_t)t * DC * DC + i * DC + j]; s2 += Qp[(size_t)t * DC * DC + j * DC + i]; }
+          Pt[e] = 0.5 * (s + s2);
+        }
       }
-      for (int c = 0; c < NR; ++c) {
-        for (int i = 0; i < M; ++i) { double s = 0.0; for (int l = 0; l < M; ++l) s -= Qi[i * M + l] * qu[l][c]; kt[i * NR + c] = s; }
-        for (int i = 0; i < N; ++i) { double s = qx[i][c]; for (int l = 0; l < M; ++l) s += Qx[l * N + i] * kt[l * NR + c]; pt[i * NR + c] = s; }
+      for (int e = lane; e < N * nc; e += 32) {
+        const int i = e / nc, c = e - i * nc;
+        double s = sQv[i * NR + c];
+#pragma unroll
+        for (int l = 0; l < M; ++l) s += Qx[l * N + i] * kt[l * NR + c];
+        pt[i * NR + c] = s;
       }
+      __syncwarp();
     }
-    // forward: terminal response of every right-hand side, then the multipliers nu of the terminal equality
-    double xs[N][NR];
-    for (int i = 0; i < N; ++i) for (int c = 0; c < NR; ++c) xs[i][c] = 0.0;
+    // ---- forward: terminal response of the right-hand sides (double-buffered in sXs), then the multipliers nu
+    for (int e = lane; e < N * NR; e += 32) sXs[e] = 0.0;
+    __syncwarp();
     for (int t = 0; t < T - 1; ++t) {
       const double* Kt = Km + (size_t)t * M * N;
       const double* kt = kk + (size_t)t * M * NR;
-      double us[M][NR], xn[N][NR];
-      for (int c = 0; c < NR; ++c)
-        for (int i = 0; i < M; ++i) { double s = kt[i * NR + c]; for (int l = 0; l < N; ++l) s += Kt[i * N + l] * xs[l][c]; us[i][c] = s; }
-      for (int c = 0; c < NR; ++c)
-        for (int i = 0; i < N; ++i) {
-          double s = (c == 0) ? ct[(size_t)t * N + i] : 0.0;
-          for (int l = 0; l < N; ++l) s += Am[i * N + l] * xs[l][c];
-          for (int l = 0; l < M; ++l) s += Bm[i * M + l] * us[l][c];
-          xn[i][c] = s;
+      const double* xs = sXs + (t & 1) * N * NR;
+      double* xn = sXs + ((t + 1) & 1) * N * NR;
+      for (int e = lane; e < M * nc; e += 32) {
+        const int i = e / nc, c = e - i * nc;
+        double s = kt[i * NR + c];
+#pragma unroll
+        for (int l = 0; l < N; ++l) s += Kt[i * N + l] * xs[l * NR + c];
+        sUs[i * NR + c] = s;
+      }
+      __syncwarp();
+      for (int e = lane; e < N * nc; e += 32) {
+        const int i = e / nc, c = e - i * nc;
+        double s = (c == 0) ? ct[(size_t)t * N + i] : 0.0;
+#pragma unroll
+        for (int l = 0; l < N; ++l) s += Am[i * N + l] * xs[l * NR + c];
+#pragma unroll
+        for (int l = 0; l < M; ++l) s += Bm[i * M + l] * sUs[l * NR + c];
+        xn[i * NR + c] = s;
+      }
+      __syncwarp();
+    }
+    {
+      const double* xs = sXs + ((T - 1) & 1) * N * NR;
+      if (with_matrix)
+        for (int e = lane; e < N * N; e += 32) { const int i = e / N, j = e - i * N; sMt[e] = xs[i * NR + 1 + j]; }
+      __syncwarp();
+      // solve  Mt nu = -xs[:,0]   (terminal step must be zero: d_{T-1} is exact from the start), partial pivoting
+      if (lane == 0) {
+        double Aug[N][N + 1], nu[N];
+        for (int i = 0; i < N; ++i) { for (int j = 0; j < N; ++j) Aug[i][j] = sMt[i * N + j]; Aug[i][N] = -xs[i * NR]; }
+        for (int c = 0; c < N; ++c) {
+          int pv = c; double best = fabs(Aug[c][c]);
+          for (int r = c + 1; r < N; ++r) if (fabs(Aug[r][c]) > best) { best = fabs(Aug[r][c]); pv = r; }
+          if (pv != c) for (int j = 0; j <= N; ++j) { const double tt = Aug[c][j]; Aug[c][j] = Aug[pv][j]; Aug[pv][j] = tt; }
+          const double dgn = (best > 1e-300) ? Aug[c][c] : 1e-300;
+          for (int r = c + 1; r < N; ++r) { const double f = Aug[r][c] / dgn; for (int j = c; j <= N; ++j) Aug[r][j] -= f * Aug[c][j]; }
+          Aug[c][c] = dgn;
         }
-      for (int i = 0; i < N; ++i) for (int c = 0; c < NR; ++c) xs[i][c] = xn[i][c];
+        for (int i = N - 1; i >= 0; --i) { double v = Aug[i][N]; for (int j = i + 1; j < N; ++j) v -= Aug[i][j] * nu[j]; nu[i] = v / Aug[i][i]; }
+        for (int i = 0; i < N; ++i) sNu[i] = nu[i];
+      }
+      __syncwarp();
     }
-    // solve  Mt nu = -xs[:,0]   (terminal step must be zero: d_{T-1} is exact from the start), partial pivoting
-    double Aug[N][N + 1], nu[N];
-    for (int i = 0; i < N; ++i) { for (int j = 0; j < N; ++j) Aug[i][j] = xs[i][1 + j]; Aug[i][N] = -xs[i][0]; }
-    for (int c = 0; c < N; ++c) {
-      int pv = c; double best = fabs(Aug[c][c]);
-      for (int r = c + 1; r < N; ++r) if (fabs(Aug[r][c]) > best) { best = fabs(Aug[r][c]); pv = r; }
-      if (pv != c) for (int j = 0; j <= N; ++j) { const double tt = Aug[c][j]; Aug[c][j] = Aug[pv][j]; Aug[pv][j] = tt; }
-      const double dgn = (best > 1e-300) ? Aug[c][c] : 1e-300;
-      for (int r = c + 1; r < N; ++r) { const double f = Aug[r][c] / dgn; for (int j = c; j <= N; ++j) Aug[r][j] -= f * Aug[c][j]; }
-      Aug[c][c] = dgn;
+    // ---- combined gains (parallel over t): kc_t = k_t[:,0] + k_t[:,1:] nu,  pc_t = p_t[:,0] + p_t[:,1:] nu  (into column 0)
+    {
+      double nu[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) nu[i] = sNu[i];
+      for (int e = lane; e < T * (M + N); e += 32) {
+        const int t = e / (M + N), r = e - t * (M + N);
+        if (r < M) {
+          if (t < T - 1) {
+            const double* kt = kk + (size_t)t * M * NR + r * NR;
+            double s = kt[0];
+#pragma unroll
+            for (int c = 0; c < N; ++c) s += kt[1 + c] * nu[c];
+            out_w[t * M + r] = s;
+          } else {
+            out_w[t * M + r] = 0.0;
+          }
+        } else {
+          const int i = r - M;
+          const double* pt = pp + (size_t)t * N * NR + i * NR;
+          double s = pt[0];
+#pragma unroll
+          for (int c = 0; c < N; ++c) s += pt[1 + c] * nu[c];
+          pin[t * N + i] = s;
+        }
+      }
+      __syncwarp();
     }
-    for (int i = N - 1; i >= 0; --i) { double v = Aug[i][N]; for (int j = i + 1; j < N; ++j) v -= Aug[i][j] * nu[j]; nu[i] = v / Aug[i][i]; }
-    // combined forward rollout + costates
-    double xc[N];
-    for (int i = 0; i < N; ++i) xc[i] = 0.0;
+    // ---- rollout (sequential in t, two stages per step): w_t = kc_t + K_t d_t ; d_{t+1} = c~_t + A d_t + B w_t ; pi_t += P_t d_t
+    if (lane < N) out_d[lane] = 0.0;
+    __syncwarp();
     for (int t = 0; t < T; ++t) {
-      const double* pt = pp + (size_t)t * N * NR;
-      const double* Pt = Pm + (size_t)t * N * N;
-      for (int i = 0; i < N; ++i) {
-        out_d[t * N + i] = xc[i];
-        double s = pt[i * NR];
-        for (int c = 0; c < N; ++c) s += pt[i * NR + 1 + c] * nu[c];
+      const double* xc = out_d + t * N;
+      if (lane < M) {
+        if (t < T - 1) {
+          const double* Kt = Km + (size_t)t * M * N;
+          double s = out_w[t * M + lane];
+#pragma unroll
+          for (int l = 0; l < N; ++l) s += Kt[lane * N + l] * xc[l];
+          out_w[t * M + lane] = s;
+        }
+      } else if (lane < M + N) {
+        const int i = lane - M;
+        const double* Pt = Pm + (size_t)t * N * N;
+        double s = pin[t * N + i];
+#pragma unroll
         for (int l = 0; l < N; ++l) s += Pt[i * N + l] * xc[l];
         pin[t * N + i] = s;
       }
+      __syncwarp();
       if (t == T - 1) break;
-      const double* Kt = Km + (size_t)t * M * N;
-      const double* kt = kk + (size_t)t * M * NR;
-      double uc[M], xn[N];
-      for (int i = 0; i < M; ++i) {
-        double s = kt[i * NR];
-        for (int c = 0; c < N; ++c) s += kt[i * NR + 1 + c] * nu[c];
-        for (int l = 0; l < N; ++l) s += Kt[i * N + l] * xc[l];
-        uc[i] = s; out_w[t * M + i] = s;
+      if (lane < N) {
+        double s = ct[(size_t)t * N + lane];
+#pragma unroll
+        for (int l = 0; l < N; ++l) s += Am[lane * N + l] * xc[l];
+#pragma unroll
+        for (int l = 0; l < M; ++l) s += Bm[lane * M + l] * out_w[t * M + l];
+        out_d[(t + 1) * N + lane] = s;
       }
-      for (int i = 0; i < N; ++i) {
-        double s = ct[(size_t)t * N + i];
-        for (int l = 0; l < N; ++l) s += Am[i * N + l] * xc[l];
-        for (int l = 0; l < M; ++l) s += Bm[i * M + l] * uc[l];
-        xn[i] = s;
-      }
-      for (int i = 0; i < N; ++i) xc[i] = xn[i];
+      __syncwarp();
     }
-    for (int j = 0; j < M; ++j) out_w[(T - 1) * M + j] = 0.0;
   };
 
   // ---- IPM iterations ---------------------------------------------------------------------------------------------
@@ -532,7 +680,7 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
         obj_prev = gl[6];
         if ((int)gl[0] == 1) { status = SCVX_ST_OPTIMAL; break; }
         if ((int)gl[0] == 2) { status = SCVX_ST_NUMERICAL; break; }
-        if (tid == 0) riccati(true, dda, dwa);
+        if (tid < 32) riccati(true, dda, dwa);
         __syncthreads();
       } else if (mode == 1) {
         const int ops[9] = {0, 0, 0, 0, 2, 2, 0, 0, 0};
@@ -547,7 +695,7 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
         __syncthreads();
       } else if (mode == 2) {
         __syncthreads();
-        if (tid == 0) riccati(false, dd, dw);
+        if (tid < 32) riccati(false, dd, dw);
         __syncthreads();
       } else if (mode == 3) {
         double bad = 0.0;
@@ -811,7 +959,7 @@ sbar_qp_kernel(int n_robots, int T, int nq, double rho, double c_S, const double
 
 template <int N, int M>
 size_t lti_smem_bytes(int T) {
-  return ((size_t)T * LtiDims<N, M>::PER_T + 32 + 9 * 12 + N * N + N * M) * sizeof(double);
+  return ((size_t)T * LtiDims<N, M>::PER_T + 32 + 9 * 12 + N * N + N * M + LtiDims<N, M>::SCR) * sizeof(double);
 }
 
 template <int N, int M>

@@ -28,9 +28,14 @@ print(json.dumps({"workload": "dist_scvx_3d.x_traj_opt, shipped scenario (3 robo
 R = 256
 i = np.arange(R) + 0.5; phi = np.arccos(1 - 2 * i / R); th = np.pi * (1 + 5 ** 0.5) * i
 pts = 9.0 * np.stack([np.cos(th) * np.sin(phi), np.sin(th) * np.sin(phi), np.cos(phi)], axis=1) + np.array([10.0, 9.5, 10.0])
-Xs = np.stack([np.linspace(np.concatenate([p, np.zeros(6)]), np.concatenate([2 * np.array([10.0, 9.5, 10.0]) - p, np.zeros(6)]), 51) for p in pts])
+# goals: the antipode rotated by 30 degrees about z -- exact antipodes would put all robots AT the centre at mid time
+# (coincident positions: the scripts' collision normal has no epsilon in its denominator and is NaN there)
+ctr = np.array([10.0, 9.5, 10.0]); ca, sa = np.cos(np.pi / 6), np.sin(np.pi / 6)
+Rz = np.array([[ca, -sa, 0.0], [sa, ca, 0.0], [0.0, 0.0, 1.0]])
+goals = ctr - (pts - ctr) @ Rz.T
+Xs = np.stack([np.linspace(np.concatenate([p, np.zeros(6)]), np.concatenate([g, np.zeros(6)]), 51) for p, g in zip(pts, goals)])
 Xd = torch.as_tensor(Xs).cuda()
-xdes = np.stack([np.concatenate([2 * np.array([10.0, 9.5, 10.0]) - p, np.zeros(3)]) for p in pts])
+xdes = np.stack([np.concatenate([g, np.zeros(3)]) for g in goals])
 def big():
     h, g = _engine.collision_tables(Xd[:, :, :3].contiguous(), 0.5)
     return _engine.solve_robot_qps(M3.Ad, M3.Bd, Xd, xdes, 0.25, 1.0, ((-1.0, 22.0), (-1.0, 20.0)), col_h=h, col_g=g, c_S=1e4)
