@@ -4,8 +4,8 @@ the ALGORITHMIC bytes / fp64 flops of the launch (DESIGN.md section 4 states the
 launches are captured (tools/ncu_all_report.py turns the report into profiles/*_all_kernels_ncu.md).
 
     python tools/prof_all_kernels.py > gpurun_out/all_plain.log
-    ncu --set full --clock-control none --import-source on -k "regex:$(python tools/prof_all_kernels.py --regex)" \
-        -o gpurun_out/all_r1k python tools/prof_all_kernels.py --once
+    ncu --set full --clock-control none --import-source on --profile-from-start off \
+        -k "regex:$(python tools/prof_all_kernels.py --regex)" -o gpurun_out/all_r1k python tools/prof_all_kernels.py --once
 """
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
@@ -34,7 +34,11 @@ def timed(name, fn, alg_bytes=None, alg_flops=None, note=""):
     if not ONCE:
         fn(); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if ONCE:
+        torch.cuda.synchronize(); torch.cuda.profiler.start()      # ncu --profile-from-start off: only these launches are captured
     a.record(); r = fn(); b.record(); torch.cuda.synchronize()
+    if ONCE:
+        torch.cuda.profiler.stop()
     ms = a.elapsed_time(b)
     rec = {"kernel": name, "ms": ms, "note": note}
     if alg_bytes is not None:
@@ -133,7 +137,7 @@ timed("warm_start_kernel<2>", lambda: _device.warm_start(_lib.MODEL_UNICYCLE, tw
 
 # ---------------------------------------------------------------- inter-sample clearance: 256 agents x K = 50 x 3 discs
 ni, Ki = 256, 50
-eng_i = BatchedSCvx(models[:ni], Ki, max_iter=3)
+eng_i = BatchedSCvx(models[:ni], Ki, max_iter=15)       # run the outer loop far enough that the trajectories really move (sigma >> 0)
 out_i = eng_i.solve(early_exit=False)
 Xi, Ui, si_ = out_i["X"], out_i["U"], out_i["sigma"]
 oc = torch.as_tensor(np.array([[c for c, _ in ob][:3] for _, _, ob in scenes[:ni]]), device=dev)
@@ -162,6 +166,7 @@ h3, g3 = _engine.collision_tables(Xd3[:, :, :3].contiguous(), M3.R)
 r3 = timed("lti_qp_kernel<6,3>", lambda: _engine.solve_robot_qps(M3.Ad, M3.Bd, Xd3, xdes3, 0.25, 1.0, ((-1.0, 22.0), (-1.0, 20.0)), col_h=h3, col_g=g3, c_S=1e4),
            note=f"the script's {Xd3.shape[0]} robots, T={M3.T}, collision rows with one slack per step")
 print(json.dumps({"lti_qp<6,3> status": r3[2].tolist(), "iters": r3[3].tolist()}))
-M2.x_traj_opt({k: v.copy() for k, v in X2.items()}, 0.25, n_admm=1)      # sbar_enum_kernel + collision tables of the 2-D script
-torch.cuda.synchronize()
+timed("ADMM_decentralized.x_traj_opt, one sweep: lti_qp_kernel<4,2> (4 robots) + sbar_enum_kernel",
+      lambda: M2.x_traj_opt({k: v.copy() for k, v in X2.items()}, 0.25, n_admm=1))
+print(json.dumps({"intersample sigma (min, median, max)": [float(si_.min()), float(si_.median()), float(si_.max())]}))
 print(json.dumps({"done": True}))
