@@ -7,7 +7,8 @@
 //                                 in [eps, dt - eps], bisection (<= 30 halvings, |b - a| < tol), keep 0 < t* < dt with phi2 > 0
 //   linearize_h          :75-97   h0 and the central-difference gradient in x_k.  grad_u is identically ZERO in the reference
 //                                 (the segment flow ignores its control argument), and is written as zeros here.
-// One WARP per (agent, segment, obstacle): lanes share the grid samples, the few bisections run warp-uniform.
+// One WARP per (agent, segment, obstacle): lanes share the grid samples; each bisection runs five halvings per round on the
+// 32 lanes (the same decisions as the reference's sequential bisection), phi2 and the linearisation one flow per lane.
 // The flow is RK4 in the normalised interval time (the FOH kernel's integrator, stopped at the fraction t).
 #include "common.cuh"
 
@@ -102,14 +103,39 @@ intersample_kernel(int n_agents, int K, int Mobs, int m, const double* __restric
   for (int i = 0; i + 1 < num_samples; ++i) {           // warp-uniform: every lane walks the same candidates
     const double p0 = phis[i], p1 = phis[i + 1];
     if (!(p0 == 0.0 || p0 * p1 < 0.0)) continue;
+    // The reference's bisection (<= 30 halvings, stop once |b - a| < tol), five halvings per round: the midpoints five
+    // halvings can visit are the 31 interior points of a 32-way split of [a, b], so lane j evaluates phi there (lane 0: phi(a))
+    // and the decisions "phi(a) phi(c) <= 0 ? b = c : a = c" are then replayed on the stored values.
     double a = ts(i), b = ts(i + 1);
-    for (int it = 0; it < 30; ++it) {
-      const double c = 0.5 * (a + b);
-      if (sg.phi(a, eps) * sg.phi(c, eps) <= 0.0) b = c; else a = c;
-      if (fabs(b - a) < tol) break;
+    {
+      int halvings = 0;
+      bool done = false;
+      while (!done && halvings < 30) {
+        const double wd = (b - a) * (1.0 / 32.0);
+        const double P = sg.phi(a + (double)lane * wd, eps);
+        int lo = 0, hi = 32;
+        for (int lvl = 0; lvl < 5 && halvings < 30; ++lvl) {
+          const int c = (lo + hi) >> 1;
+          const double pl = __shfl_sync(0xffffffffu, P, lo), pc = __shfl_sync(0xffffffffu, P, c);
+          if (pl * pc <= 0.0) hi = c; else lo = c;
+          ++halvings;
+          if (fabs((double)(hi - lo) * wd) < tol) { done = true; break; }
+        }
+        const double a2 = a + (double)lo * wd, b2 = (hi == 32) ? b : a + (double)hi * wd;
+        a = a2; b = b2;
+      }
     }
     const double r = 0.5 * (a + b);
-    if (!(0.0 < r && r < t_range) || !(sg.phi2(r, eps) > 0.0)) continue;
+    if (!(0.0 < r && r < t_range)) continue;
+    {
+      // phi2(r) > 0 (intersample_collision.py:66-70): its four clearance evaluations on lanes 0..3
+      const double tq = (lane & 2) ? r - eps : r + eps;
+      const double hq = (lane < 4) ? sg.h(sg.x, (lane & 1) ? tq - eps : tq + eps) : 0.0;
+      const double h0p = __shfl_sync(0xffffffffu, hq, 0), h1p = __shfl_sync(0xffffffffu, hq, 1);
+      const double h2p = __shfl_sync(0xffffffffu, hq, 2), h3p = __shfl_sync(0xffffffffu, hq, 3);
+      const double ph_p = (h0p - h1p) / (2.0 * eps), ph_m = (h2p - h3p) / (2.0 * eps);
+      if (!((ph_p - ph_m) / (2.0 * eps) > 0.0)) continue;
+    }
     if (found < max_roots) {
       // linearize_h at (x_k, t*): lanes 0..2*NX-1 take the perturbed states, lane 31 the nominal one
       double xs[NX];

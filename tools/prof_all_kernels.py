@@ -4,16 +4,23 @@ the ALGORITHMIC bytes / fp64 flops of the launch (DESIGN.md section 4 states the
 launches are captured (tools/ncu_all_report.py turns the report into profiles/*_all_kernels_ncu.md).
 
     python tools/prof_all_kernels.py > gpurun_out/all_plain.log
-    ncu --set full --clock-control none --import-source on --profile-from-start off \
-        -k "regex:$(python tools/prof_all_kernels.py --regex)" -o gpurun_out/all_r1k python tools/prof_all_kernels.py --once
+    ncu --metrics $(python tools/prof_all_kernels.py --metrics) --clock-control none --profile-from-start off \
+        -k "regex:$(python tools/prof_all_kernels.py --regex)" --csv --log-file gpurun_out/all_metrics.csv python tools/prof_all_kernels.py --once
+(a targeted metric list, a few replay passes per launch: `--set full` over all ~40 launches costs 6+ GPU-minutes and a 90 MB report)
 """
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 
 KERNEL_REGEX = ("foh_rk4|integrate_|linearize_|ipm_kernel|outer_update|order_by_iters|consensus_kernel|lti_qp|sbar_|"
                 "slab_normals|warm_start|min_pair|min_obstacle|intersample|clearance_samples|cross_min")
+METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,"
+           "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,"
+           "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,"
+           "smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,launch__registers_per_thread,launch__shared_mem_per_block_dynamic")
 if "--regex" in sys.argv:
     print(KERNEL_REGEX); sys.exit(0)
+if "--metrics" in sys.argv:
+    print(METRICS); sys.exit(0)
 
 import numpy as np, torch
 from scvx_b200 import _device, _lib
@@ -136,8 +143,8 @@ timed("warm_start_kernel<2>", lambda: _device.warm_start(_lib.MODEL_UNICYCLE, tw
       alg_bytes=nw * 8 * (6 + 3 * Mw + 5 * Kw), note=f"{nw} agents x K={Kw} x M={Mw}")
 
 # ---------------------------------------------------------------- inter-sample clearance: 256 agents x K = 50 x 3 discs
-ni, Ki = 256, 50
-eng_i = BatchedSCvx(models[:ni], Ki, max_iter=15)       # run the outer loop far enough that the trajectories really move (sigma >> 0)
+ni, Ki = 64, 50
+eng_i = BatchedSCvx(models[:ni], Ki, max_iter=10)       # run the outer loop far enough that the trajectories really move (sigma >> 0)
 out_i = eng_i.solve(early_exit=False)
 Xi, Ui, si_ = out_i["X"], out_i["U"], out_i["sigma"]
 oc = torch.as_tensor(np.array([[c for c, _ in ob][:3] for _, _, ob in scenes[:ni]]), device=dev)
