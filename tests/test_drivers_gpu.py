@@ -101,6 +101,31 @@ def test_batched_scvx_matches_host_loop_first_iteration_and_invariants(cuda):
     assert (out["sigma"] >= -1e-12).all() and (out["tr_radius"] == 50.0).all()
 
 
+def test_pipelined_scvx_is_identical_to_batched(cuda):
+    """Lanes on separate streams change the ORDER of execution only: iterates, metrics and interior-point iteration counts
+    equal those of one launch over all agents, bit for bit (ragged last lane, early exit off and on)."""
+    import torch
+    from scvx_b200.batch import BatchedSCvx, PipelinedSCvx
+    from scvx_b200.models.unicycle_model import UnicycleModel
+    rng = np.random.default_rng(3)
+    models = []
+    for _ in range(7):
+        y = rng.uniform(-8, 8)
+        models.append(UnicycleModel(r_init=np.array([-8.5, y, 0.0]), r_final=np.array([8.5, -y, 0.0]),
+                                    obstacles=[([float(rng.uniform(-4, 4)), float(rng.uniform(-4, 4))], float(rng.uniform(0.5, 1.5)))]))
+    ref = BatchedSCvx(models, K, max_iter=5).solve(early_exit=False)
+    pipe = PipelinedSCvx(models, K, n_lanes=3, max_iter=5)           # lanes of 3, 3, 1 agents
+    assert [b - a for a, b in pipe.bounds] == [3, 3, 1]
+    out = pipe.solve(early_exit=False, check_every=2)
+    torch.cuda.synchronize()
+    assert out["n_outer"] == 5 and pipe.launches == 3 * 5 * 5
+    for key in ("X", "U", "sigma", "tr_radius", "active", "metrics"):
+        assert torch.equal(out[key], ref[key]), key
+    assert torch.equal(pipe.ipm_iters(), ref["ipm_iters"][-1]) and (pipe.status() == 0).all()
+    # more lanes than agents collapses to one agent per lane
+    assert len(PipelinedSCvx(models[:2], K, n_lanes=8, max_iter=1).engines) == 2
+
+
 def test_batched_scvx_converged_agent_keeps_previous_iterate(cuda):
     """Drive one agent to the fixed point by restarting from its own solution with a tiny trust region, and
     check the reference's break-before-accept quirk (scvx_solver.py:104-111) on the device path."""
