@@ -560,9 +560,10 @@ __device__ __forceinline__ constexpr double gG(int r, int i) {
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <class M>
+// JSM: the interval Jacobians live in shared memory (compile-time, so that their loads are LDS and not generic LD)
+template <class M, bool JSM>
 __global__ void __launch_bounds__(SOLVER_MAX_THREADS, 1)
-ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int jac_in_smem, size_t jac_ws_offset) {
+ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, size_t jac_ws_offset) {
   using Dm = Dims<M>;
   constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
   constexpr int NSP = Dm::NSP, SD = Dm::SD, SR = Dm::SR, NJ = Dm::NJ, STG = Dm::STG, NPLAIN = Dm::NPLAIN;
@@ -584,7 +585,7 @@ ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, int j
   double* red = gl + 64;                // [9][24] reduction scratch
   double* ST = Ck;                      // per-interval staging of the assembly pass (16 of SD doubles)
   // interval Jacobians [K][NJ]: shared memory when it fits, else a slice of the global workspace
-  double* JAC = jac_in_smem ? (red + 9 * 24) : ((double*)a.workspace + jac_ws_offset + (size_t)agent * K * NJ);
+  double* JAC = JSM ? (red + 9 * 24) : ((double*)a.workspace + jac_ws_offset + (size_t)agent * K * NJ);
   // globals: gl[0..3] = sigma, t_nu, t_x, t_u ; gl[4..7] = dg_aff ; gl[8..11] = dg ; gl[12..14] sG ; gl[15..17] lG ;
   // gl[18..33] = Gg/S 4x4 ; gl[34..37] = bg ; gl[40] flag ; gl[41] alpha_p ; gl[42] alpha_d ; gl[43] sigmu ; gl[44] mu
   // gl[45] comp ; gl[46..49] Y'b scratch
@@ -1791,13 +1792,15 @@ int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
     snprintf(g_last_error, sizeof(g_last_error), "K=%d needs %zu B of shared memory per agent (> 227 KB)", a.K, smem);
     return SCVX_E_UNSUPPORTED;
   }
-  cudaError_t e = cudaFuncSetAttribute(ipm_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = jac_smem ? cudaFuncSetAttribute(ipm_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(ipm_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   int threads = ((a.K + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > SOLVER_MAX_THREADS) threads = SOLVER_MAX_THREADS;
   const size_t jac_off = solver_ws_doubles_per_agent<M>(a.K, a.M + a.n_nbr) * (size_t)a.n_agents;
-  ipm_kernel<M><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_smem ? 1 : 0, jac_off);
+  if (jac_smem) ipm_kernel<M, true><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
+  else ipm_kernel<M, false><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
   SCVX_CHECK_LAUNCH("scvx_solve_batched");
   return SCVX_OK;
 }
