@@ -22,7 +22,7 @@ _FAR = 1.0e3                     # padding obstacle: centre far outside the work
 
 
 class AgentBatch:
-    def __init__(self, models, K, device=None):
+    def __init__(self, models, K, device=None, min_obstacles=0):
         if not models:
             raise ValueError("empty agent batch")
         mid = models[0].device_model_id
@@ -33,7 +33,9 @@ class AgentBatch:
         self.n_x, self.n_u, self.d = _device.MODEL_DIMS[mid]
         self.device = torch.device("cuda") if device is None else torch.device(device)
         tabs = [m.get_constraints() for m in models]
-        self.M = max(len(t.obs_clearance) for t in tabs)
+        # obstacle slots per agent: the largest count in the batch (or `min_obstacles`: lanes of one batch pad alike);
+        # missing obstacles are padded with discs far outside the workspace that never become active
+        self.M = max(max(len(t.obs_clearance) for t in tabs), int(min_obstacles))
         n, M, d = self.n, self.M, self.d
         obs_c = np.full((n, M, d), _FAR)
         obs_clear = np.full((n, M), -_FAR)
@@ -177,7 +179,11 @@ class PipelinedSCvx:
         per = (n + n_lanes - 1) // n_lanes
         self.bounds = [(a, min(a + per, n)) for a in range(0, n, per)]
         self.n, self.K, self.max_iter = n, K, max_iter
-        self.engines = [BatchedSCvx(models[a:b], K, max_iter=max_iter, device=device, **kw) for a, b in self.bounds]
+        # every lane pads its obstacle table to the batch-wide maximum, so a lane solves exactly the problems the single
+        # launch would (padding rows are inactive but do enter the interior-point iterates in the last bits)
+        m_all = max(len(m.get_constraints().obs_clearance) for m in models)
+        self.engines = [BatchedSCvx(None, K, max_iter=max_iter, device=device,
+                                    batch=AgentBatch(models[a:b], K, device, min_obstacles=m_all), **kw) for a, b in self.bounds]
         self.device = self.engines[0].batch.device
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.engines]
         self.state = None

@@ -113,9 +113,11 @@ def test_pipelined_scvx_is_identical_to_batched(cuda):
         y = rng.uniform(-8, 8)
         models.append(UnicycleModel(r_init=np.array([-8.5, y, 0.0]), r_final=np.array([8.5, -y, 0.0]),
                                     obstacles=[([float(rng.uniform(-4, 4)), float(rng.uniform(-4, 4))], float(rng.uniform(0.5, 1.5)))]))
+    models[-1] = UnicycleModel(r_init=np.array([-8.5, 0.5, 0.0]), r_final=np.array([8.5, -0.5, 0.0]), obstacles=[])
     ref = BatchedSCvx(models, K, max_iter=5).solve(early_exit=False)
-    pipe = PipelinedSCvx(models, K, n_lanes=3, max_iter=5)           # lanes of 3, 3, 1 agents
-    assert [b - a for a, b in pipe.bounds] == [3, 3, 1]
+    pipe = PipelinedSCvx(models, K, n_lanes=3, max_iter=5)           # lanes of 3, 3, 1 agents; the last lane's only agent has
+    assert [b - a for a, b in pipe.bounds] == [3, 3, 1]              # no obstacle and is padded like the whole batch
+    assert [e.batch.M for e in pipe.engines] == [1, 1, 1]
     out = pipe.solve(early_exit=False, check_every=2)
     torch.cuda.synchronize()
     assert out["n_outer"] == 5 and pipe.launches == 3 * 5 * 5
