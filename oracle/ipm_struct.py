@@ -62,7 +62,11 @@ def spd_inverse_frozen(Dj, piv_tol=1e-12, reg_rel=0.0):
 
 
 class StructIPM:
-    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False, linalg="cr", step_frac=0.999, uncapped=False):
+    def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False, linalg="cr", step_frac=0.999, uncapped=False,
+                 gondzio=0, g_thresh=0.5, g_delta=0.3):
+        # gondzio > 0: EXPERIMENT, not in the kernel: up to `gondzio` centrality correctors after a Mehrotra step whose
+        # min(alpha_p, alpha_d) < g_thresh; n_solves counts the linear solves (2 per iteration + 1 per corrector tried)
+        self.gondzio, self.g_thresh, self.g_delta, self.n_solves = int(gondzio), float(g_thresh), float(g_delta), 0
         self.p, self.verbose, self.linalg = p, verbose, linalg
         self.step_frac, self.uncapped = step_frac, uncapped
         self.mu0, self.max_iter, self.eps_gap, self.eps_feas = mu0, max_iter, eps_gap, eps_feas
@@ -271,6 +275,27 @@ class StructIPM:
             ap, ad = maxstep(S, dS, cap), maxstep(L, dL, cap)
             if self.qrho > 0 or self.ball:
                 ap = ad = min(ap, ad)
+            self.n_solves += 2
+            for _g in range(self.gondzio):
+                # Gondzio's centrality corrector: look a little further along the direction, project the complementarity products
+                # of that trial point onto [0.1, 10] x the target, and re-solve with the projection error folded into the
+                # second-order term (the Newton system is linear in it: one more solve with the same factorisation)
+                if min(ap, ad) >= self.g_thresh:
+                    break
+                tp, td = min(1.0, ap + self.g_delta), min(1.0, ad + self.g_delta)
+                mut = sg * mu
+                cc_g = []
+                for v, dv, l, dl_, c_ in zip(S, dS, L, dL, cc):
+                    vt = (v + tp * dv) * (l + td * dl_)
+                    cc_g.append(c_ - np.maximum(np.clip(vt, 0.1 * mut, 10.0 * mut) - vt, -10.0 * mut))
+                cand = newton(sg * mu, *cc_g)
+                self.n_solves += 1
+                ap_g, ad_g = maxstep(S, cand[3], cap), maxstep(L, cand[4], cap)
+                if self.qrho > 0 or self.ball:
+                    ap_g = ad_g = min(ap_g, ad_g)
+                if ap_g + ad_g <= 1.01 * (ap + ad):
+                    break
+                (dW, dg, dxi, dS, dL), ap, ad, cc = cand, ap_g, ad_g, cc_g
             ap, ad = min(1.0, self.step_frac * ap), min(1.0, self.step_frac * ad)
             W = W + ap * dW; sig += ap * dg[0]; t_nu += ap * dg[1]; t_x += ap * dg[2]; t_u += ap * dg[3]
             xi = xi + ap * np.where(hfree, dxi, 0.0)
