@@ -36,7 +36,8 @@ struct LtiDims {
                                + N                // ctil (equality residual)
                                + N * N + M * N + M * N + M * M   // P, K, Qux, Quu^-1
                                + M * NR + N * NR                // k, p (all right-hand sides)
-                               + N + M;                         // best primal-feasible iterate seen
+                               + N + M                          // best primal-feasible iterate seen
+                               + N * NR;                        // state response to every right-hand-side column (xsT)
   // scratch of the warp-cooperative Riccati sweeps: PA, PB, Quu, pc, qu, qx, xs (two buffers), us, Mt, nu
   static constexpr int SCR = N * N + N * M + M * M + N * NR + M * NR + N * NR + 2 * N * NR + M * NR + N * N + N;
 };
@@ -75,7 +76,8 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
   double* pp = kk + (size_t)T * M * NR;   // [T][N*NR]
   double* dbest = pp + (size_t)T * N * NR;   // [T][N]
   double* wbest = dbest + (size_t)T * N;     // [T][M]
-  double* gl = wbest + (size_t)T * M;     // [32]
+  double* xsT = wbest + (size_t)T * M;    // [T][N*NR]
+  double* gl = xsT + (size_t)T * N * NR;  // [32]
   double* red = gl + 32;                  // [9][12]
   double* AB = red + 9 * 12;              // A [N*N], B [N*M]
   double* Am = AB;
@@ -312,14 +314,15 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
       }
       __syncwarp();
     }
-    // ---- forward: terminal response of the right-hand sides (double-buffered in sXs), then the multipliers nu
-    for (int e = lane; e < N * NR; e += 32) sXs[e] = 0.0;
+    // ---- forward: response of the state to every right-hand-side column, KEPT for all t (xsT); the terminal one gives nu
+    if (with_matrix)
+      for (int e = lane; e < N * NR; e += 32) xsT[e] = 0.0;                 // x_0 = 0 in every column
     __syncwarp();
     for (int t = 0; t < T - 1; ++t) {
       const double* Kt = Km + (size_t)t * M * N;
       const double* kt = kk + (size_t)t * M * NR;
-      const double* xs = sXs + (t & 1) * N * NR;
-      double* xn = sXs + ((t + 1) & 1) * N * NR;
+      const double* xs = xsT + (size_t)t * N * NR;
+      double* xn = xsT + (size_t)(t + 1) * N * NR;
       for (int e = lane; e < M * nc; e += 32) {
         const int i = e / nc, c = e - i * nc;
         double s = kt[i * NR + c];
@@ -340,14 +343,11 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
       __syncwarp();
     }
     {
-      const double* xs = sXs + ((T - 1) & 1) * N * NR;
-      if (with_matrix)
-        for (int e = lane; e < N * N; e += 32) { const int i = e / N, j = e - i * N; sMt[e] = xs[i * NR + 1 + j]; }
-      __syncwarp();
-      // solve  Mt nu = -xs[:,0]   (terminal step must be zero: d_{T-1} is exact from the start), partial pivoting
+      const double* xs = xsT + (size_t)(T - 1) * N * NR;
+      // solve  Mt nu = -xs[:,0], Mt = xs[:,1:]   (terminal step must be zero: d_{T-1} is exact from the start), partial pivoting
       if (lane == 0) {
         double Aug[N][N + 1], nu[N];
-        for (int i = 0; i < N; ++i) { for (int j = 0; j < N; ++j) Aug[i][j] = sMt[i * N + j]; Aug[i][N] = -xs[i * NR]; }
+        for (int i = 0; i < N; ++i) { for (int j = 0; j < N; ++j) Aug[i][j] = xs[i * NR + 1 + j]; Aug[i][N] = -xs[i * NR]; }
         for (int c = 0; c < N; ++c) {
           int pv = c; double best = fabs(Aug[c][c]);
           for (int r = c + 1; r < N; ++r) if (fabs(Aug[r][c]) > best) { best = fabs(Aug[r][c]); pv = r; }
@@ -361,64 +361,46 @@ __global__ void __launch_bounds__(128, 1) lti_qp_kernel(scvx_lti_args a) {
       }
       __syncwarp();
     }
-    // ---- combined gains (parallel over t): kc_t = k_t[:,0] + k_t[:,1:] nu,  pc_t = p_t[:,0] + p_t[:,1:] nu  (into column 0)
+    // ---- superposition, parallel over t (no sequential rollout): d_t = xs_t[:,0] + xs_t[:,1:] nu, then
+    //      w_t = k_t[:,0] + k_t[:,1:] nu + K_t d_t  and  pi_t = p_t[:,0] + p_t[:,1:] nu + P_t d_t
     {
       double nu[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) nu[i] = sNu[i];
+      for (int e = lane; e < T * N; e += 32) {
+        const double* xr = xsT + (size_t)e * NR;            // row (t, i) of the stored responses
+        double s = xr[0];
+#pragma unroll
+        for (int c = 0; c < N; ++c) s += xr[1 + c] * nu[c];
+        out_d[e] = s;
+      }
+      __syncwarp();
       for (int e = lane; e < T * (M + N); e += 32) {
         const int t = e / (M + N), r = e - t * (M + N);
+        const double* xc = out_d + t * N;
         if (r < M) {
+          double s = 0.0;
           if (t < T - 1) {
             const double* kt = kk + (size_t)t * M * NR + r * NR;
-            double s = kt[0];
+            const double* Kt = Km + (size_t)t * M * N + r * N;
+            s = kt[0];
 #pragma unroll
             for (int c = 0; c < N; ++c) s += kt[1 + c] * nu[c];
-            out_w[t * M + r] = s;
-          } else {
-            out_w[t * M + r] = 0.0;
+#pragma unroll
+            for (int l = 0; l < N; ++l) s += Kt[l] * xc[l];
           }
+          out_w[t * M + r] = s;
         } else {
           const int i = r - M;
           const double* pt = pp + (size_t)t * N * NR + i * NR;
+          const double* Pt = Pm + (size_t)t * N * N + i * N;
           double s = pt[0];
 #pragma unroll
           for (int c = 0; c < N; ++c) s += pt[1 + c] * nu[c];
+#pragma unroll
+          for (int l = 0; l < N; ++l) s += Pt[l] * xc[l];
           pin[t * N + i] = s;
         }
-      }
-      __syncwarp();
-    }
-    // ---- rollout (sequential in t, two stages per step): w_t = kc_t + K_t d_t ; d_{t+1} = c~_t + A d_t + B w_t ; pi_t += P_t d_t
-    if (lane < N) out_d[lane] = 0.0;
-    __syncwarp();
-    for (int t = 0; t < T; ++t) {
-      const double* xc = out_d + t * N;
-      if (lane < M) {
-        if (t < T - 1) {
-          const double* Kt = Km + (size_t)t * M * N;
-          double s = out_w[t * M + lane];
-#pragma unroll
-          for (int l = 0; l < N; ++l) s += Kt[lane * N + l] * xc[l];
-          out_w[t * M + lane] = s;
-        }
-      } else if (lane < M + N) {
-        const int i = lane - M;
-        const double* Pt = Pm + (size_t)t * N * N;
-        double s = pin[t * N + i];
-#pragma unroll
-        for (int l = 0; l < N; ++l) s += Pt[i * N + l] * xc[l];
-        pin[t * N + i] = s;
-      }
-      __syncwarp();
-      if (t == T - 1) break;
-      if (lane < N) {
-        double s = ct[(size_t)t * N + lane];
-#pragma unroll
-        for (int l = 0; l < N; ++l) s += Am[lane * N + l] * xc[l];
-#pragma unroll
-        for (int l = 0; l < M; ++l) s += Bm[lane * M + l] * out_w[t * M + l];
-        out_d[(t + 1) * N + lane] = s;
       }
       __syncwarp();
     }
