@@ -164,6 +164,15 @@ class BatchedSCvx:
                 "was_active": was_active[:done], "n_outer": done}
 
 
+def lane_bounds(n, n_lanes):
+    """Contiguous lanes of ceil(n / n_lanes) agents (the last one ragged); never more lanes than agents."""
+    if n <= 0:
+        raise ValueError("empty agent batch")
+    n_lanes = max(1, min(int(n_lanes), n))
+    per = (n + n_lanes - 1) // n_lanes
+    return [(a, min(a + per, n)) for a in range(0, n, per)]
+
+
 class PipelinedSCvx:
     """`BatchedSCvx` over `n_lanes` sub-batches of the agents, each advancing its own outer loop on its own CUDA stream.
 
@@ -175,9 +184,7 @@ class PipelinedSCvx:
 
     def __init__(self, models, K, n_lanes=4, max_iter=MAX_ITER, device=None, **kw):
         n = len(models)
-        n_lanes = max(1, min(int(n_lanes), n))
-        per = (n + n_lanes - 1) // n_lanes
-        self.bounds = [(a, min(a + per, n)) for a in range(0, n, per)]
+        self.bounds = lane_bounds(n, n_lanes)
         self.n, self.K, self.max_iter = n, K, max_iter
         # every lane pads its obstacle table to the batch-wide maximum, so a lane solves exactly the problems the single
         # launch would (padding rows are inactive but do enter the interior-point iterates in the last bits)

@@ -63,3 +63,19 @@ def test_single_process_is_identity():
     X = torch.zeros((3, 3, 4)); U = torch.ones((3, 2, 4))
     Xa, Ua = allgather_shards(X, U, 3, 3, None, None)
     assert Xa is X and Ua is U
+
+
+def test_lane_bounds_of_the_pipelined_driver():
+    """Lanes of PipelinedSCvx: contiguous, cover every agent once, ragged tail, never more lanes than agents."""
+    import pytest
+    from scvx_b200.batch import lane_bounds
+    assert lane_bounds(1024, 4) == [(0, 256), (256, 512), (512, 768), (768, 1024)]
+    assert lane_bounds(7, 3) == [(0, 3), (3, 6), (6, 7)]
+    assert lane_bounds(2, 8) == [(0, 1), (1, 2)]
+    assert lane_bounds(5, 1) == [(0, 5)] and lane_bounds(5, 0) == [(0, 5)]
+    for n in (1, 9, 100, 1000):
+        for lanes in (1, 2, 3, 4, 7, 16):
+            b = lane_bounds(n, lanes)
+            assert b[0][0] == 0 and b[-1][1] == n and all(x[1] == y[0] for x, y in zip(b, b[1:])) and len(b) <= max(1, min(lanes, n))
+    with pytest.raises(ValueError):
+        lane_bounds(0, 4)
