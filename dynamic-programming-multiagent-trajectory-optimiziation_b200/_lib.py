@@ -33,7 +33,7 @@ class SolveArgs(ctypes.Structure):
         ("X", _c_dp), ("U", _c_dp), ("nu", _c_dp), ("sigma", _c_dp), ("s_prime", _c_dp), ("col_slack", _c_dp),
         ("objective", _c_dp), ("status", _c_dp), ("iters", _c_dp),
         ("workspace", _c_dp), ("workspace_bytes", ctypes.c_ulonglong),
-        ("quad_diag", _c_dp), ("lin_w", _c_dp), ("quad_pair", _c_dp), ("fix_sigma", _c_int), ("block_order", _c_dp),
+        ("quad_diag", _c_dp), ("lin_w", _c_dp), ("quad_pair", _c_dp), ("fix_sigma", _c_int), ("block_order", _c_dp), ("mu0", _c_dp),
     ]
 
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "scvx_linearize_collision_indexed": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),
     "scvx_slab_normals_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_int] + [_c_dp] * 7 + [_c_dp]),
     "scvx_order_by_iters": (_c_int, [_c_int, _c_dp, _c_dp, _c_dp]),
+    "scvx_mu0_from_iters": (_c_int, [_c_int, _c_dp, _c_int, ctypes.c_double, ctypes.c_double, _c_dp, _c_dp]),
     "scvx_solve_workspace_bytes": (ctypes.c_ulonglong, [_c_int, _c_int, _c_int, _c_int, _c_int]),
     "scvx_solve_batched": (_c_int, [ctypes.POINTER(SolveArgs), _c_dp]),
     "scvx_consensus_update": (_c_int, [_c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),

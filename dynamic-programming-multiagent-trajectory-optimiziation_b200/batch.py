@@ -69,8 +69,12 @@ class BatchedSCvx:
 
     def __init__(self, models, K, max_iter=MAX_ITER, tr_radius0=TRUST_RADIUS0, conv_tol=CONV_TOL,
                  weight_nu=WEIGHT_NU, weight_slack=WEIGHT_SLACK, weight_sigma=WEIGHT_SIGMA, n_sub=0,
-                 ipm_max_iter=0, device=None, batch=None):
+                 ipm_max_iter=0, device=None, batch=None, adaptive_mu0=False):
         self.batch = batch if batch is not None else AgentBatch(models, K, device)
+        # adaptive_mu0: agents whose previous sub-problem took <= 10 interior-point iterations start the next one at mu = 0.1
+        # instead of 10 (measured on the numpy twin only so far, hence off by default)
+        self.adaptive_mu0 = bool(adaptive_mu0)
+        self._mu0 = None
         b = self.batch
         self.K, self.max_iter, self.tr_radius0, self.conv_tol = K, max_iter, tr_radius0, conv_tol
         self.weight_nu, self.weight_slack, self.weight_sigma = weight_nu, weight_slack, weight_sigma
@@ -84,6 +88,7 @@ class BatchedSCvx:
         self.launches = 0
         self._order = None            # longest-first block order from the previous iteration's IPM iteration counts
         self._order_buf = torch.empty(n, dtype=torch.int32, device=dev)
+        self._mu0_buf = torch.empty(n, dtype=F64, device=dev)
 
     def iterate(self, X, U, sigma, tr, active, metrics_row, solver_events=None):
         """One outer iteration, in place on (X, U, sigma, tr, active): 5 kernel launches (FOH, obstacle linearisation, sub-problem,
@@ -97,10 +102,13 @@ class BatchedSCvx:
             solver_events[0].record(torch.cuda.current_stream())
         _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
                                  b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
-                                 self.weight_sigma, max_iter=self.ipm_max_iter, block_order=self._order)
+                                 self.weight_sigma, max_iter=self.ipm_max_iter, block_order=self._order, mu0=self._mu0)
         if solver_events is not None:
             solver_events[1].record(torch.cuda.current_stream())
         self._order = _device.order_by_iters(self.ws.iters, out=self._order_buf)
+        if self.adaptive_mu0:
+            self._mu0 = _device.mu0_from_iters(self.ws.iters, out=self._mu0_buf)
+            self.launches += 1
         _device.outer_update(b.model_id, b.M, self.conv_tol, self.ws.X, self.ws.U, self.ws.nu, self.ws.sigma,
                              self.ws.s_prime, X, U, sigma, tr, active, metrics_row)
         self.launches += 5 if b.M else 4

@@ -563,13 +563,16 @@ __device__ __forceinline__ constexpr double gG(int r, int i) {
 // JSM: the interval Jacobians live in shared memory (compile-time, so that their loads are LDS and not generic LD)
 template <class M, bool JSM>
 __global__ void __launch_bounds__(SOLVER_MAX_THREADS, 1)
-ipm_kernel(scvx_solve_args a, double mu0, double eps_gap, double eps_feas, size_t jac_ws_offset) {
+ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_feas, size_t jac_ws_offset) {
   using Dm = Dims<M>;
   constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
   constexpr int NSP = Dm::NSP, SD = Dm::SD, SR = Dm::SR, NJ = Dm::NJ, STG = Dm::STG, NPLAIN = Dm::NPLAIN;
   constexpr bool BALL = Dm::BALL;
   const int K = a.K, agent = a.block_order ? a.block_order[blockIdx.x] : (int)blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
   const int Mobs = a.M, NH = a.M + a.n_nbr;
+  // start value of the barrier parameter: per agent when the caller provides one (scvx_mu0_from_iters), else the default
+  const double mu0_agent = a.mu0 ? a.mu0[agent] : 0.0;
+  const double mu0 = (mu0_agent > 0.0) ? mu0_agent : mu0_default;
 
   extern __shared__ __align__(16) double smem[];
   PHASE_INIT();
@@ -1839,6 +1842,23 @@ __global__ void __launch_bounds__(256) order_by_iters_kernel(int n, const int* _
     rank += (v > mine || (v == mine && j < i)) ? 1 : 0;
   }
   order[rank] = i;
+}
+
+__global__ void __launch_bounds__(256) mu0_from_iters_kernel(int n, const int* __restrict__ iters, int easy_max, double mu_easy,
+                                                             double mu_hard, double* __restrict__ mu0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) mu0[i] = (iters[i] > 0 && iters[i] <= easy_max) ? mu_easy : mu_hard;
+}
+
+extern "C" int scvx_mu0_from_iters(int n_agents, const int* iters, int easy_max_iters, double mu0_easy, double mu0_hard, double* mu0,
+                                   void* stream) {
+  if (n_agents < 0) return bad_arg("n_agents");
+  if (n_agents == 0) return SCVX_OK;
+  if (!iters || !mu0) return bad_arg("null pointer");
+  if (!(mu0_easy > 0.0) || !(mu0_hard > 0.0)) return bad_arg("mu0 values must be positive");
+  mu0_from_iters_kernel<<<(n_agents + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n_agents, iters, easy_max_iters, mu0_easy, mu0_hard, mu0);
+  SCVX_CHECK_LAUNCH("scvx_mu0_from_iters");
+  return SCVX_OK;
 }
 
 extern "C" int scvx_order_by_iters(int n_agents, const int* iters, int* order, void* stream) {
