@@ -55,3 +55,15 @@ def test_args_structs_match_header(cname, pyname):
         stmt = re.sub(r"^(const\s+)?(unsigned\s+long\s+long|unsigned\s+char|double|int|void)\s*", "", stmt)
         fields += [f.strip().lstrip("*").strip() for f in stmt.split(",")]
     assert fields == [f[0] for f in getattr(_lib, pyname)._fields_]
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md's entry-point table names every function include/scvx_b200.h declares."""
+    import os, re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "scvx_b200.h")).read()
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    names = set(re.findall(r"^(?:int|unsigned long long|const char\*)\s+(scvx_[a-z0-9_]+)\(", hdr, flags=re.M))
+    assert len(names) >= 25
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
