@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscvx_b200.so")
 SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "lti_qp.cu", "utils.cu", "intersample.cu", "probe.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+OBJ_DIR = os.path.join(HERE, "build")          # object files (git-ignored); only the .so sits next to the package
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -22,7 +22,8 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "scvx_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "scvx_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -30,12 +31,13 @@ def build(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared object next to this file."""
     if not force and not needs_build():
         return LIB
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + os.environ.get("SCVX_NVCC_EXTRA", "").split()
+    flags = NVCC_FLAGS + os.environ.get("SCVX_NVCC_EXTRA", "").split()
+    os.makedirs(OBJ_DIR, exist_ok=True)
     objs = []
     procs = []
     for s in SOURCES:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        obj = os.path.join(OBJ_DIR, s.replace(".cu", ".o"))
         cmd = [_nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libscvx_b200.so")
+# SCVX_LIB selects an instrumented build of the same sources (e.g. -DSCVX_PHASE_TIMING, tools/phase_timing.py); never a fallback
+LIB_PATH = os.environ.get("SCVX_LIB") or os.path.join(HERE, "libscvx_b200.so")
 
 MODEL_UNICYCLE = 0
 MODEL_SINGLE_INTEGRATOR = 1

@@ -206,7 +206,7 @@ class PipelinedSCvx:
 
     @property
     def launches(self):
-        return sum(e.launches for e in self.engines)
+        return getattr(self, "_launch_base", 0) + sum(e.launches for e in self.engines)
 
     def start(self, X0=None, U0=None, initial_sigma=1.0, tr_radius0=None):
         """Per-lane iterate (X, U, sigma, trust radius, active flags) and the metrics record of every outer iteration."""
@@ -227,24 +227,76 @@ class PipelinedSCvx:
         torch.cuda.current_stream(self.device).synchronize()
         return self
 
-    def run(self, n_iter):
-        """Enqueue n_iter outer iterations of every lane (lane-major round robin per iteration, so the host feeds all
-        streams evenly) and make the CALLING stream wait for all of them; no host synchronisation."""
+    def _fork(self):
         main = torch.cuda.current_stream(self.device)
         go = torch.cuda.Event(); go.record(main)
         for st in self.streams:
             st.wait_event(go)
+        return main
+
+    def _join(self, main):
+        for st in self.streams:
+            done = torch.cuda.Event(); done.record(st)
+            main.wait_event(done)
+
+    def run(self, n_iter):
+        """Enqueue n_iter outer iterations of every lane (lane-major round robin per iteration, so the host feeds all
+        streams evenly) and make the CALLING stream wait for all of them; no host synchronisation."""
+        if self.it + n_iter > self.max_iter:
+            raise ValueError("PipelinedSCvx.run: more iterations than max_iter")
+        main = self._fork()
         for k in range(n_iter):
             it = self.it + k
-            if it >= self.max_iter:
-                raise ValueError("PipelinedSCvx.run: more iterations than max_iter")
             for eng, st, (X, U, sig, tr, act, met) in zip(self.engines, self.streams, self.state):
                 with torch.cuda.stream(st):
                     eng.iterate(X, U, sig, tr, act, met[it])
         self.it += n_iter
-        for st in self.streams:
-            done = torch.cuda.Event(); done.record(st)
-            main.wait_event(done)
+        self._join(main)
+
+    # -- CUDA-graph replay: the host stops pacing the 5 launches x n_lanes of every step ----------------------------------
+    def build_graph(self, steps_per_graph=1):
+        """Capture `steps_per_graph` outer iterations of ALL lanes (forked onto the lane streams, joined at the end) into one
+        CUDA graph.  Every pointer a step uses is fixed (iterate, workspaces, block-order buffers), so a replay is exactly
+        the launches `run` would make; the per-step metrics land in a fixed staging table that `run_graph` copies into the
+        history.  One eager step runs first if none has yet (the block-order pointer of the first solve is NULL)."""
+        if self.state is None:
+            raise RuntimeError("PipelinedSCvx.build_graph: call start() first")
+        if any(e._order is None for e in self.engines):
+            self.run(1)
+        self._gsteps = int(steps_per_graph)
+        self._gmet = [torch.zeros((self._gsteps, c - a, 6), dtype=F64, device=self.device) for a, c in self.bounds]
+        torch.cuda.current_stream(self.device).synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        launches0 = self.launches
+        with torch.cuda.graph(graph, stream=side):
+            main = self._fork()
+            for k in range(self._gsteps):
+                for eng, st, gm, (X, U, sig, tr, act, _met) in zip(self.engines, self.streams, self._gmet, self.state):
+                    with torch.cuda.stream(st):
+                        eng.iterate(X, U, sig, tr, act, gm[k])
+            self._join(main)
+        self._graph = graph
+        self._graph_launches = self.launches - launches0      # kernels per replay (capturing launched none of them)
+        for e in self.engines:
+            e.launches = 0
+        self._launch_base = launches0
+        return self
+
+    def run_graph(self, n_iter, keep_history=True):
+        """n_iter outer iterations by graph replay (n_iter must be a multiple of the captured steps_per_graph)."""
+        if n_iter % self._gsteps:
+            raise ValueError("PipelinedSCvx.run_graph: n_iter must be a multiple of steps_per_graph")
+        if self.it + n_iter > self.max_iter:
+            raise ValueError("PipelinedSCvx.run_graph: more iterations than max_iter")
+        for _ in range(n_iter // self._gsteps):
+            self._graph.replay()
+            self._launch_base += self._graph_launches
+            if keep_history:
+                for gm, s in zip(self._gmet, self.state):
+                    s[5][self.it:self.it + self._gsteps].copy_(gm, non_blocking=True)
+            self.it += self._gsteps
 
     # -- host-buffer API: the call a user holding pinned numpy/torch host arrays makes -------------------------------
     def make_host_buffers(self):
@@ -271,22 +323,46 @@ class PipelinedSCvx:
         pinned host arrays to the device, runs the step's kernels and copies the new iterate + metrics back, all on the
         lane's stream (a lane's next upload is ordered after its previous download, so the host arrays always carry the
         latest iterate); the call returns when everything has landed on the host."""
-        main = torch.cuda.current_stream(self.device)
-        go = torch.cuda.Event(); go.record(main)
-        for st in self.streams:
-            st.wait_event(go)
+        main = self._fork()
         for _ in range(n_steps):
-            for eng, st, d, (a, c) in zip(self.engines, self.streams, self._dbuf, self.bounds):
-                with torch.cuda.stream(st):
-                    for k in ("X", "U", "sigma", "tr", "active"):
-                        d[k].copy_(host[k][a:c], non_blocking=True)
-                    eng.iterate(d["X"], d["U"], d["sigma"], d["tr"], d["active"], d["metrics"])
-                    for k in ("X", "U", "sigma", "tr", "active", "metrics"):
-                        host[k][a:c].copy_(d[k], non_blocking=True)
-        for st in self.streams:
-            done = torch.cuda.Event(); done.record(st)
-            main.wait_event(done)
+            self._enqueue_host_step(host)
+        self._join(main)
         main.synchronize()
+        return host
+
+    def _enqueue_host_step(self, host):
+        for eng, st, d, (a, c) in zip(self.engines, self.streams, self._dbuf, self.bounds):
+            with torch.cuda.stream(st):
+                for k in ("X", "U", "sigma", "tr", "active"):
+                    d[k].copy_(host[k][a:c], non_blocking=True)
+                eng.iterate(d["X"], d["U"], d["sigma"], d["tr"], d["active"], d["metrics"])
+                for k in ("X", "U", "sigma", "tr", "active", "metrics"):
+                    host[k][a:c].copy_(d[k], non_blocking=True)
+
+    def build_host_graph(self, host):
+        """`run_host(host, 1)` as one CUDA graph: per lane the H2D copies of its slice, the step's kernels and the D2H copies
+        (memcpy nodes on pinned memory), forked over the lane streams.  Replay with `run_host_graph`."""
+        if any(e._order is None for e in self.engines):
+            self.run_host(host, 1)
+        torch.cuda.current_stream(self.device).synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        launches0 = self.launches
+        with torch.cuda.graph(graph, stream=side):
+            main = self._fork()
+            self._enqueue_host_step(host)
+            self._join(main)
+        self._hgraph, self._hgraph_launches = graph, self.launches - launches0
+        for e in self.engines:
+            e.launches = 0
+        self._launch_base = launches0
+        return self
+
+    def run_host_graph(self, host, n_steps=1):
+        for _ in range(n_steps):
+            self._hgraph.replay()
+            self._launch_base += self._hgraph_launches
+        torch.cuda.current_stream(self.device).synchronize()
         return host
 
     def gather(self):

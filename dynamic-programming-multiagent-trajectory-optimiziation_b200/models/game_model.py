@@ -50,13 +50,27 @@ class GameUnicycleModel(UnicycleModel):
         self.z_params = [z[j] for j in range(z.shape[0])]
         self.z_degenerate = int(deg[0].item())
 
+    @staticmethod
+    def _horizon_of(first_neighbour, X_v, X_prev, neighbour_prev_pos):
+        """Number of knots when the model has no obstacle slack to read it from: the shape of whatever trajectory-like
+        argument is at hand.  The arguments may be `.shape`-carrying holders (AgentBestResponse passes those), not arrays,
+        so np.asarray must not be applied to them."""
+        candidates = [first_neighbour, X_v, X_prev] + list(neighbour_prev_pos or [])
+        for c in candidates:
+            shape = getattr(c, "shape", None)
+            if shape is None and c is not None and not hasattr(c, "value"):
+                shape = np.shape(c)
+            if shape is not None and len(shape) == 2:
+                return int(shape[1])
+        raise ValueError("GameUnicycleModel.get_cost_function: cannot infer the number of knots from its arguments")
+
     def get_cost_function(self, X_v=None, U_v=None, neighbour_pos=None, X_prev=None, neighbour_prev_pos=None):  # noqa: ARG002
         """Cost descriptor (game_model.py:69-126): control effort, control-rate and curvature smoothing, inertia, path
         length; (re)initialises the slab normals to zero when the neighbour count changed, like the reference's lazy init."""
         n_nbr = 0 if neighbour_pos is None else len(neighbour_pos)
         K = self.s_prime[0].shape[0] if self.s_prime else None
         if not self.z_params or len(self.z_params) != n_nbr:
-            Kz = K if K is not None else (np.asarray(neighbour_pos[0]).shape[1] if n_nbr else 0)
+            Kz = K if K is not None else (self._horizon_of(neighbour_pos[0], X_v, X_prev, neighbour_prev_pos) if n_nbr else 0)
             self.z_params = [np.zeros((2, Kz)) for _ in range(n_nbr)]
         self.extra_constraints = [{"kind": "slab", "neighbour": j, "radius": self.collision_radius} for j in range(n_nbr)]
         return {"control_weight": self.control_weight, "control_rate_weight": self.control_rate_weight,
