@@ -62,7 +62,7 @@ struct Dims {
   static constexpr int SD = (NS * NS) | 1;                // padded block stride (odd)
   static constexpr int SR = (NS * 4) | 1;                 // padded border stride (odd)
   static constexpr int STG = SD;                          // per-interval staging (16 used) ALIASES factor slot C
-  static constexpr int ST2 = 3;                           // corrector staging (e'tau of the interval)
+  static constexpr int ST2 = 3;                           // corrector staging (e'tau of the interval, sigma-mu coefficient; the rest rides in dW)
   static constexpr int PER_STAGE = 3 * NSP + NJ + 3 * SD + SR + ST2;
   static constexpr int PER_STAGE_NOJAC = 3 * NSP + 3 * SD + SR + ST2;
   static constexpr int SMALL = 64 + 9 * 24;               // globals + reduction scratch
@@ -99,11 +99,23 @@ struct HingeData {
   bool on;
 };
 
-struct AgentPtrs {
+// Row state of one agent in the global workspace: multipliers of the plain rows, the stored slack of the (nonlinear) ball row,
+// and (slack, two multipliers) of every hinge pair, plus the PENDING STEP of the hinge pairs.  The step-length pass (S) keeps the
+// plain rows' step in registers across its block reduction and updates their multipliers in place once the step length is known;
+// a stage's hinge pairs are too many for that (up to hundreds with inter-agent rows), so their step is left in `d*` and the
+// next residual pass (R) applies it on the fly.  (A first fused version double-buffered the whole state: 3x the footprint, the
+// 1024-agent working set fell out of L2 and the passes stalled on DRAM -- profiles/r02_ipm_kernel_ncu.md.)
+struct RowState {
   double *lP;                          // [NPLAIN][K]  multipliers of the plain rows
-  double *sB;                          // [K]          stored slack of the (nonlinear) ball row, single integrator only
   double *xi, *l1, *l2;                // [NH][K]      hinge slack and the two multipliers of each hinge pair
+  double *sB;                          // [K]          stored slack of the ball row, single integrator only
 };
+struct AgentPtrs { RowState s; double *dxi, *dl1, *dl2; };
+
+// Store that the compiler does not treat as a possible alias of ordinary loads (no "memory" clobber).  Every use below stores
+// to an address that the same thread has already loaded in the same pass (data dependence orders the two) and that no thread
+// loads again before the next block barrier; with plain stores every later load of the stage would be ordered behind them.
+__device__ __forceinline__ void st_na(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v)); }
 
 // ---- per-stage linear forms ----------------------------------------------------------------------
 // nu-like combination for interval k: Jn w_{k+1} + Jp w_k + Js g_sigma (- zbar if AFFINE)
@@ -629,10 +641,13 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 
   AgentPtrs ws;
   {
-    double* base = (double*)a.workspace + (size_t)agent * ((size_t)K * (NPLAIN + 3 * NH + (BALL ? 1 : 0)));
-    ws.lP = base;
-    ws.xi = ws.lP + (size_t)NPLAIN * K; ws.l1 = ws.xi + (size_t)NH * K; ws.l2 = ws.l1 + (size_t)NH * K;
-    ws.sB = ws.l2 + (size_t)NH * K;
+    const size_t per = (size_t)K * (NPLAIN + 6 * (size_t)NH + (BALL ? 1 : 0));
+    double* base = (double*)a.workspace + (size_t)agent * per;
+    ws.s.lP = base; ws.s.xi = ws.s.lP + (size_t)NPLAIN * K; ws.s.l1 = ws.s.xi + (size_t)NH * K; ws.s.l2 = ws.s.l1 + (size_t)NH * K;
+    ws.s.sB = ws.s.l2 + (size_t)NH * K;
+    ws.dxi = ws.s.sB + (BALL ? K : 0); ws.dl1 = ws.dxi + (size_t)NH * K; ws.dl2 = ws.dl1 + (size_t)NH * K;
+    // no step is pending before the first iteration: zero deltas (and step lengths, below)
+    for (size_t i = tid; i < 3 * (size_t)NH * K; i += nthr) ws.dxi[i] = 0.0;
   }
   auto hinge_a = [&](int h, int c, int k) -> double {
     return (h < Mobs) ? obs_a[((size_t)h * D + c) * K + k] : col_a[((size_t)(h - Mobs) * D + c) * K + k];
@@ -642,18 +657,34 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   };
   auto hinge_on = [&](int h) -> bool { return (h < Mobs) || !col_mask || col_mask[h - Mobs]; };
   auto hinge_w = [&](int h) -> double { return (h < Mobs) ? sc.hw_obs : sc.hw_col; };
-  auto load_hinge = [&](int h, int k) -> HingeData<D> {
+  auto load_hinge_ab = [&](int h, int k) -> HingeData<D> {
     HingeData<D> r;
     r.on = (h < NH) && hinge_on(h);
     r.b = 0.0; r.xi = 1.0; r.l1 = 1.0; r.l2 = 1.0;
 #pragma unroll
     for (int c = 0; c < D; ++c) r.a[c] = 0.0;
     if (r.on) {
-      const size_t o = (size_t)h * K + k;
 #pragma unroll
       for (int c = 0; c < D; ++c) r.a[c] = hinge_a(h, c, k);
       r.b = hinge_b(h, k);
-      r.xi = ws.xi[o]; r.l1 = ws.l1[o]; r.l2 = ws.l2[o];
+    }
+    return r;
+  };
+  auto load_hinge = [&](int h, int k, const RowState& src) -> HingeData<D> {
+    HingeData<D> r = load_hinge_ab(h, k);
+    if (r.on) {
+      const size_t o = (size_t)h * K + k;
+      r.xi = src.xi[o]; r.l1 = src.l1[o]; r.l2 = src.l2[o];
+    }
+    return r;
+  };
+  // residual pass: the pending step of the hinge pair is applied, in place
+  auto load_hinge_apply = [&](int h, int k, double al_p, double al_d) -> HingeData<D> {
+    HingeData<D> r = load_hinge_ab(h, k);
+    if (r.on) {
+      const size_t o = (size_t)h * K + k;
+      r.xi = fma(al_p, ws.dxi[o], ws.s.xi[o]); r.l1 = fma(al_d, ws.dl1[o], ws.s.l1[o]); r.l2 = fma(al_d, ws.dl2[o], ws.s.l2[o]);
+      st_na(ws.s.xi + o, r.xi); st_na(ws.s.l1 + o, r.l1); st_na(ws.s.l2 + o, r.l2);
     }
     return r;
   };
@@ -744,6 +775,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       gl[0] = sig0; gl[1] = red[0] * 1.1 + 1.0; gl[2] = red[1] + sc.r_tr * 0.25; gl[3] = red[2] + sc.r_tr * 0.25;
       const double sG[3] = {sc.r_tr - gl[2] - gl[3] - (sig0 - sc.sig_ref), sc.r_tr - gl[2] - gl[3] + (sig0 - sc.sig_ref), sig0};
       for (int r = 0; r < 3; ++r) { gl[12 + r] = fmax(sG[r], 1e-8); gl[15 + r] = mu0 / gl[12 + r]; }
+      gl[41] = 0.0; gl[42] = 0.0;            // no step pending for the first residual pass
     }
     __syncthreads();
   }
@@ -761,7 +793,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
         for (int i = 0; i < NX; ++i) f += sgn(e, i) * nu[i];
         const double s = fmax(-f, 1e-8);
-        ws.lP[(size_t)(Dm::R_NU + e) * K + k] = mu0 / s;
+        ws.s.lP[(size_t)(Dm::R_NU + e) * K + k] = mu0 / s;
       }
     }
 #pragma unroll
@@ -770,7 +802,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
       for (int i = 0; i < NX; ++i) f += sgn(e, i) * (w[i] - WR(k, i));
       const double s = fmax(-f, 1e-8);
-      ws.lP[(size_t)(Dm::R_X + e) * K + k] = mu0 / s;
+      ws.s.lP[(size_t)(Dm::R_X + e) * K + k] = mu0 / s;
     }
 #pragma unroll
     for (int e = 0; e < NEU; ++e) {
@@ -778,29 +810,29 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
       for (int j = 0; j < NU; ++j) f += sgn(e, j) * (w[NX + j] - WR(k, NX + j));
       const double s = fmax(-f, 1e-8);
-      ws.lP[(size_t)(Dm::R_U + e) * K + k] = mu0 / s;
+      ws.s.lP[(size_t)(Dm::R_U + e) * K + k] = mu0 / s;
     }
     if (fr) {
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         double s = fmax(sc.pos_hi - w[i], 1e-8);
-        ws.lP[(size_t)(Dm::R_P + i) * K + k] = mu0 / s;
+        ws.s.lP[(size_t)(Dm::R_P + i) * K + k] = mu0 / s;
         s = fmax(w[i] - sc.pos_lo, 1e-8);
-        ws.lP[(size_t)(Dm::R_P + D + i) * K + k] = mu0 / s;
+        ws.s.lP[(size_t)(Dm::R_P + D + i) * K + k] = mu0 / s;
       }
       if (!BALL) {
         const double sv[4] = {sc.v_max - w[NX], w[NX], sc.w_max - w[NX + 1], sc.w_max + w[NX + 1]};
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           const double s = fmax(sv[r], 1e-8);
-          ws.lP[(size_t)(Dm::R_V + r) * K + k] = mu0 / s;
+          ws.s.lP[(size_t)(Dm::R_V + r) * K + k] = mu0 / s;
         }
       } else {
         double n2 = 0.0;
 #pragma unroll
         for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
         const double s = fmax(0.5 * (sc.v_max * sc.v_max - n2), 1e-8);
-        ws.sB[k] = s; ws.lP[(size_t)Dm::R_V * K + k] = mu0 / s;
+        ws.s.sB[k] = s; ws.s.lP[(size_t)Dm::R_V * K + k] = mu0 / s;
       }
       for (int h = 0; h < NH; ++h) {
         if (!hinge_on(h)) continue;
@@ -812,7 +844,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
         const double num = (viol >= 0.0) ? hw * viol + disc : 4.0 * mu0 * mu0 / fmax(disc - hw * viol, 1e-300);
         const double xi = (num + 2.0 * mu0) / (2.0 * hw);
         const size_t o = (size_t)h * K + k;
-        ws.xi[o] = xi; ws.l1[o] = mu0 / (xi - viol); ws.l2[o] = mu0 / xi;
+        ws.s.xi[o] = xi; ws.s.l1[o] = mu0 / (xi - viol); ws.s.l2[o] = mu0 / xi;
       }
     }
   }
@@ -830,20 +862,22 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   const int max_iter = a.max_iter > 0 ? a.max_iter : 80;
 
   // =================================================================================================
-  // A row pass.  MODE 0: residuals + Newton matrix staging + predictor rhs staging + stationarity staging
-  //              MODE 1: affine step statistics (alpha_p, alpha_d, three sums for mu_aff)
-  //              MODE 2: corrector rhs staging
-  //              MODE 3: final step lengths
-  //              MODE 4: apply the step to the row state
+  // Three row passes per iteration.  R: the pending step is applied to the row state, then residuals + Newton matrix staging +
+  //                                  predictor rhs staging + stationarity staging
+  //                               P: affine step statistics (alpha_p, alpha_d, three sums for mu_aff) + corrector rhs staging
+  //                               S: final step lengths; the row-state step is left for the next R pass
   // Per-stage results that other threads need go to ST (interval part) and dW / Dk / Rb (own stage).
   // =================================================================================================
   for (it = 0; it < max_iter; ++it) {
     double part[24];
-    // ------------------------------------------------------------------------------------ MODE 0
+    // ------------------------------------------------------------------------------------ RESIDUAL PASS (+ pending step)
 #pragma unroll
     for (int i = 0; i < 24; ++i) part[i] = 0.0;
     // part: 0 comp, 1 rp_inf, 2 rd_inf(xi), 3 Gg00, 4 Gg01, 5 Gg11, 6 Gg22, 7 Gg33, 8..11 bg(tau), 12..15 rdg(lambda), 16 obj_hinge, 17 obj_quad
     const double sig = gl[0], tnu = gl[1], tx = gl[2], tu = gl[3];
+    // The step of the PREVIOUS iteration is applied to the hinge pairs here, on the fly (the plain rows were updated by pass S).
+    const double al_p0 = gl[41], al_d0 = gl[42];
+    auto LPA = [&](size_t o) -> double { return ws.s.lP[o]; };
     for (int k = tid; k < K; k += nthr) {
       const double* w = W + k * NSP;
       const bool fr = (k > 0 && k < K - 1);
@@ -857,7 +891,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
         for (int e = 0; e < NEX; ++e) {
           const size_t o = (size_t)(Dm::R_NU + e) * K + k;
-          const double l = ws.lP[o];
+          const double l = LPA(o);
           double f = -tnu;
 #pragma unroll
           for (int i = 0; i < NX; ++i) f += sgn(e, i) * nu[i];
@@ -905,7 +939,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
         for (int e = 0; e < NEX; ++e) {
           const size_t o = (size_t)(Dm::R_X + e) * K + k;
-          const double l = ws.lP[o];
+          const double l = LPA(o);
           double f = -tx;
 #pragma unroll
           for (int i = 0; i < NX; ++i) f += sgn(e, i) * dx[i];
@@ -931,7 +965,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
         for (int e = 0; e < NEU; ++e) {
           const size_t o = (size_t)(Dm::R_U + e) * K + k;
-          const double l = ws.lP[o];
+          const double l = LPA(o);
           double f = -tu;
 #pragma unroll
           for (int j = 0; j < NU; ++j) f += sgn(e, j) * du[j];
@@ -954,11 +988,11 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
         for (int i = 0; i < D; ++i) {
           size_t o = (size_t)(Dm::R_P + i) * K + k;
-          double l = ws.lP[o], s = fmax(sc.pos_hi - w[i], TINY_S), rp = 0.0, wgt = l * rcp_fast(s);
+          double l = LPA(o), s = fmax(sc.pos_hi - w[i], TINY_S), rp = 0.0, wgt = l * rcp_fast(s);
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           Dl[i][i] += wgt; bt[i] += wgt * rp; bl[i] += l;
           o = (size_t)(Dm::R_P + D + i) * K + k;
-          l = ws.lP[o]; s = fmax(w[i] - sc.pos_lo, TINY_S); rp = 0.0; wgt = l * rcp_fast(s);
+          l = LPA(o); s = fmax(w[i] - sc.pos_lo, TINY_S); rp = 0.0; wgt = l * rcp_fast(s);
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
           Dl[i][i] += wgt; bt[i] -= wgt * rp; bl[i] -= l;
         }
@@ -967,7 +1001,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
             const size_t o = (size_t)(Dm::R_V + r) * K + k;
-            const double l = ws.lP[o], s = fmax(-gz[r], TINY_S), rp = 0.0, wgt = l * rcp_fast(s);
+            const double l = LPA(o), s = fmax(-gz[r], TINY_S), rp = 0.0, wgt = l * rcp_fast(s);
             const int c = NX + (r >> 1);
             const double sg = (r & 1) ? -1.0 : 1.0;
             part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
@@ -975,12 +1009,13 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           }
         } else {
           const size_t o = (size_t)Dm::R_V * K + k;
-          const double l = ws.lP[o];
+          const double l = LPA(o);
           double n2 = 0.0;
 #pragma unroll
           for (int j = 0; j < NU; ++j) n2 += w[NX + j] * w[NX + j];
           // the ball row is quadratic: its slack stays an independent (stored) variable, rp = c(u) + s
-          const double s = ws.sB[k], rp = 0.5 * (n2 - sc.v_max * sc.v_max) + s, wgt = l * rcp_fast(s);
+          const double s = ws.s.sB[k];
+          const double rp = 0.5 * (n2 - sc.v_max * sc.v_max) + s, wgt = l * rcp_fast(s);
           part[0] += s * l; part[1] = fmax(part[1], fabs(rp));
 #pragma unroll
           for (int i = 0; i < NU; ++i) {
@@ -1018,7 +1053,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
         for (int h0 = 0; h0 < NH; h0 += HINGE_CHUNK) {
           HingeData<D> hb[HINGE_CHUNK];
 #pragma unroll
-          for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k);
+          for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge_apply(h0 + c, k, al_p0, al_d0);
 #pragma unroll
           for (int c = 0; c < HINGE_CHUNK; ++c)
             if (hb[c].on) hinge_body0(h0 + c, hb[c]);
@@ -1318,112 +1353,117 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
     }
     __syncthreads();
 
-    // ------------------------------------------------------------------------------------ MODE 1/2/3/4
-    // A generic visitor over all rows of stage k.  For each row it provides (s, lambda, r_p, g.dz_aff, g.dz) and
-    // the address where the row state lives; F does the mode-specific work.
+    // ------------------------------------------------------------------------------------ PASS P / PASS S
+    // A generic visitor over all rows of stage k, instantiated twice (straight-line code, no per-row mode tests):
+    //   PASS 1 (P): statistics of the affine (predictor) step -- step-length ratios and the three sums for mu_aff -- AND the
+    //               corrector's right-hand side.  The row term of that right-hand side is tau = (sigma mu - ds_a dl_a + l r_p) / s,
+    //               linear in the centring target sigma mu that only the block-wide reduction of this very pass determines:
+    //               so the pass accumulates the coefficient of sigma mu (1/s) and the rest separately and combines them after
+    //               the reduction.  (The first version walked the rows a second time for this.)
+    //   PASS 3 (S): step-length ratios of the final direction; the plain rows' multiplier step stays in registers and is applied
+    //               in place once the step length is known, the hinge pairs' step goes to the d* buffers for the next R pass.
     PHASE(7);
-    // `mode` is a compile-time constant of each instantiation: every pass is straight-line code without mode tests
-    auto run_mode = [&](auto mode_c) -> bool {
-      constexpr int mode = decltype(mode_c)::value;
-      const double sigmu = gl[43];
-      const double al_p = gl[41], al_d = gl[42];
-      double pr[8];
+    auto run_pass = [&](auto pass_c) -> bool {
+      constexpr int PASS = decltype(pass_c)::value;
+      constexpr bool P = (PASS == 1);
+      const double sigmu = gl[43];                                         // valid in PASS 3 (written by the tail of PASS 1)
+      double pr[13];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) pr[i] = 0.0;
-      // pr: 0 alpha_p (min), 1 alpha_d (min), 2 sum ds*l, 3 sum s*dl, 4 sum ds*dl, 5..7 corrector bg pieces (t_nu, t_x, t_u), 8.. see below
-      double prg = 0.0;   // sigma-column piece of the corrector bg
+      for (int i = 0; i < 13; ++i) pr[i] = 0.0;
+      // pr: 0 max primal ratio, 1 max dual ratio, [P] 2 sum ds*l, 3 sum s*dl, 4 sum ds*dl, 5..7 border rhs pieces (t_nu, t_x, t_u)
+      //     multiplying sigma mu, 8..10 the same, constant part, 11 / 12 the sigma-column piece (times sigma mu / constant);
+      //     [S] 2 non-finite flag
       const double ga0 = gl[4], ga1 = gl[5], ga2 = gl[6], ga3 = gl[7];     // affine global step
-      const double gd0 = gl[8], gd1 = gl[9], gd2 = gl[10], gd3 = gl[11];   // final global step
+      const double gd0 = gl[8], gd1 = gl[9], gd2 = gl[10], gd3 = gl[11];   // final global step (PASS 3)
       // Step-length ratios without divisions: the primal ratio -ds/s reuses the row's reciprocal 1/s; the dual ratio
       // -dl/l is tracked as a fraction (qdn/qdd) compared by cross-multiplication.  alpha = min(1, 1/max ratio).
       double qp = 0.0, qdn = 0.0, qdd = 1.0;
       auto upd_d = [&](double dl, double l) { if (-dl * qdd > qdn * l) { qdn = -dl; qdd = l; } };
-      // per-row kernel: returns tau (mode 2) and updates statistics / state
-      auto row = [&](double* pl, double l, double gz_h, double gdza, double gdz, double& tau_out, double* ps = nullptr) {
+      // per-row kernel.  P: returns the two pieces of tau (ta * sigma mu + tb).  S: stores the multiplier step to `pd`
+      // (and the slack step of the nonlinear ball row to `psd`).
+      auto row = [&](double l, double gz_h, double gdza, double gdz, double& ta, double& tb, double& dl_out, const double* ps = nullptr,
+                     double* ds_out = nullptr) {
         const double s = ps ? *ps : fmax(-gz_h, TINY_S);          // stored slack only for the nonlinear ball row
         const double rs = rcp_fast(s);
         const double rp = ps ? gz_h + s : 0.0, wgt = l * rs;
         const double dsa = -rp - gdza, dla = -l - wgt * dsa;
-        if (mode == 1) {
+        const double c2 = dsa * dla;
+        if (P) {
           qp = fmax(qp, -dsa * rs); upd_d(dla, l);
-          pr[2] += dsa * l; pr[3] += s * dla; pr[4] += dsa * dla;
+          pr[2] += dsa * l; pr[3] += s * dla; pr[4] += c2;
+          ta = rs; tb = (l * rp - c2) * rs;
           return;
         }
-        const double c2 = dsa * dla;
-        if (mode == 2) { tau_out = (sigmu - c2 + l * rp) * rs; return; }
         const double ds = -rp - gdz, dl = -l + (sigmu - c2) * rs - wgt * ds;
-        if (mode == 3) { qp = fmax(qp, -ds * rs); upd_d(dl, l); return; }
-        *pl = l + al_d * dl;
-        if (ps) *ps = s + al_p * ds;
+        qp = fmax(qp, -ds * rs); upd_d(dl, l);
+        dl_out = dl;
+        if (ds_out) *ds_out = ds;
       };
+      double dlr[P ? 1 : NPLAIN], dsb = 0.0;     // S: the plain rows' multiplier step (and the ball row's slack step), in registers
+#pragma unroll
+      for (int r = 0; r < (P ? 1 : NPLAIN); ++r) dlr[r] = 0.0;
+      auto DLR = [&](int r) -> double& { return dlr[P ? 0 : r]; };
 
+      double bta[NS], btb[NS];              // own-stage rhs pieces of the corrector (P), kept in registers across the reduction
+#pragma unroll
+      for (int i = 0; i < NS; ++i) { bta[i] = 0.0; btb[i] = 0.0; }
       for (int k = tid; k < K; k += nthr) {
         const double* w = W + k * NSP;
         const double* da = dWa + k * NSP;
-        const double* dz = dW + k * NSP;       // valid in modes 3, 4 (final direction)
+        const double* dz = dW + k * NSP;       // valid in PASS 3 (final direction)
         const bool fr = (k > 0 && k < K - 1);
-        // mode 4 stores into the row state, so the compiler cannot hoist later loads above earlier stores: fetch the
-        // stage's plain-row multipliers in one batch first.  (Modes 1-3 are store-free and schedule their loads freely.)
-        double lp4[mode == 4 ? NPLAIN : 1];
-        if (mode == 4) {
-#pragma unroll
-          for (int r = 0; r < Dm::R_P; ++r) lp4[mode == 4 ? r : 0] = (r >= NEX || k < K - 1) ? ws.lP[(size_t)r * K + k] : 0.0;
-#pragma unroll
-          for (int r = Dm::R_P; r < NPLAIN; ++r) lp4[mode == 4 ? r : 0] = fr ? ws.lP[(size_t)r * K + k] : 0.0;
-        }
-        auto LP = [&](int r, size_t o) -> double { return (mode == 4) ? lp4[mode == 4 ? r : 0] : ws.lP[o]; };
-        double bt[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) bt[i] = 0.0;
         if (k < K - 1) {
           const double* jac = JAC + (size_t)k * NJ;
           double nu[NX], nua[NX], nud[NX] = {0, 0, 0};
           nu_form<Dm, true>(jac, w, w + NSP, sig, nu);
           nu_form<Dm, false>(jac, da, da + NSP, ga0, nua);
-          if (mode >= 3) nu_form<Dm, false>(jac, dz, dz + NSP, gd0, nud);
-          double et[NX] = {0, 0, 0}, stau = 0.0;
+          if (!P) nu_form<Dm, false>(jac, dz, dz + NSP, gd0, nud);
+          double eta[NX] = {0, 0, 0}, etb[NX] = {0, 0, 0}, sta = 0.0, stb = 0.0;
 #pragma unroll
           for (int e = 0; e < NEX; ++e) {
             const size_t o = (size_t)(Dm::R_NU + e) * K + k;
             double f = -tnu, fa = -ga1, fd = -gd1;
 #pragma unroll
             for (int i = 0; i < NX; ++i) { f += sgn(e, i) * nu[i]; fa += sgn(e, i) * nua[i]; fd += sgn(e, i) * nud[i]; }
-            double tau = 0.0;
-            row(ws.lP + o, LP(Dm::R_NU + e, o), f, fa, fd, tau);
-            if (mode == 2) {
-              stau += tau;
+            double ta = 0.0, tb = 0.0;
+            row(ws.s.lP[o], f, fa, fd, ta, tb, DLR(Dm::R_NU + e));
+            if (P) {
+              sta += ta; stb += tb;
 #pragma unroll
-              for (int i = 0; i < NX; ++i) et[i] += tau * sgn(e, i);
+              for (int i = 0; i < NX; ++i) { eta[i] += ta * sgn(e, i); etb[i] += tb * sgn(e, i); }
             }
           }
-          if (mode == 2) {
+          if (P) {
             const double* S = jac + NX * NX + 2 * NX * NU;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) { ST2[(size_t)k * Dm::ST2 + i] = et[i]; prg -= et[i] * S[i]; }
-            pr[5] -= stau;
+            for (int i = 0; i < NX; ++i) {
+              ST2[(size_t)k * Dm::ST2 + i] = eta[i]; dW[k * NSP + i] = etb[i];      // dW is free until the combine below
+              pr[11] -= eta[i] * S[i]; pr[12] -= etb[i] * S[i];
+            }
+            pr[5] -= sta; pr[8] -= stb;
           }
         }
         {
           double dx[NX];
 #pragma unroll
           for (int i = 0; i < NX; ++i) dx[i] = w[i] - WR(k, i);
-          double stx = 0.0;
+          double sxa = 0.0, sxb = 0.0;
 #pragma unroll
           for (int e = 0; e < NEX; ++e) {
             const size_t o = (size_t)(Dm::R_X + e) * K + k;
             double f = -tx, fa = -ga2, fd = -gd2;
 #pragma unroll
             for (int i = 0; i < NX; ++i) { f += sgn(e, i) * dx[i]; fa += sgn(e, i) * da[i]; fd += sgn(e, i) * dz[i]; }
-            double tau = 0.0;
-            row(ws.lP + o, LP(Dm::R_X + e, o), f, fa, (mode >= 3) ? fd : 0.0, tau);
-            if (mode == 2) {
-              stx += tau;
+            double ta = 0.0, tb = 0.0;
+            row(ws.s.lP[o], f, fa, P ? 0.0 : fd, ta, tb, DLR(Dm::R_X + e));
+            if (P) {
+              sxa += ta; sxb += tb;
 #pragma unroll
-              for (int i = 0; i < NX; ++i) bt[i] += tau * sgn(e, i);
+              for (int i = 0; i < NX; ++i) { bta[i] += ta * sgn(e, i); btb[i] += tb * sgn(e, i); }
             }
           }
-          pr[6] -= stx;
-          double stu = 0.0;
+          pr[6] -= sxa; pr[9] -= sxb;
+          double sua = 0.0, sub = 0.0;
 #pragma unroll
           for (int e = 0; e < NEU; ++e) {
             const size_t o = (size_t)(Dm::R_U + e) * K + k;
@@ -1432,26 +1472,26 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
             for (int j = 0; j < NU; ++j) {
               f += sgn(e, j) * (w[NX + j] - WR(k, NX + j)); fa += sgn(e, j) * da[NX + j]; fd += sgn(e, j) * dz[NX + j];
             }
-            double tau = 0.0;
-            row(ws.lP + o, LP(Dm::R_U + e, o), f, fa, (mode >= 3) ? fd : 0.0, tau);
-            if (mode == 2) {
-              stu += tau;
+            double ta = 0.0, tb = 0.0;
+            row(ws.s.lP[o], f, fa, P ? 0.0 : fd, ta, tb, DLR(Dm::R_U + e));
+            if (P) {
+              sua += ta; sub += tb;
 #pragma unroll
-              for (int j = 0; j < NU; ++j) bt[NX + j] += tau * sgn(e, j);
+              for (int j = 0; j < NU; ++j) { bta[NX + j] += ta * sgn(e, j); btb[NX + j] += tb * sgn(e, j); }
             }
           }
-          pr[7] -= stu;
+          pr[7] -= sua; pr[10] -= sub;
         }
         if (fr) {
 #pragma unroll
           for (int i = 0; i < D; ++i) {
-            double tau = 0.0;
+            double ta = 0.0, tb = 0.0;
             size_t o = (size_t)(Dm::R_P + i) * K + k;
-            row(ws.lP + o, LP(Dm::R_P + i, o), w[i] - sc.pos_hi, da[i], (mode >= 3) ? dz[i] : 0.0, tau);
-            if (mode == 2) bt[i] += tau;
+            row(ws.s.lP[o], w[i] - sc.pos_hi, da[i], P ? 0.0 : dz[i], ta, tb, DLR(Dm::R_P + i));
+            if (P) { bta[i] += ta; btb[i] += tb; }
             o = (size_t)(Dm::R_P + D + i) * K + k;
-            row(ws.lP + o, LP(Dm::R_P + D + i, o), sc.pos_lo - w[i], -da[i], (mode >= 3) ? -dz[i] : 0.0, tau);
-            if (mode == 2) bt[i] -= tau;
+            row(ws.s.lP[o], sc.pos_lo - w[i], -da[i], P ? 0.0 : -dz[i], ta, tb, DLR(Dm::R_P + D + i));
+            if (P) { bta[i] -= ta; btb[i] -= tb; }
           }
           if (!BALL) {
             const double gz[4] = {w[NX] - sc.v_max, -w[NX], w[NX + 1] - sc.w_max, -w[NX + 1] - sc.w_max};
@@ -1460,20 +1500,20 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
               const size_t o = (size_t)(Dm::R_V + r) * K + k;
               const int c = NX + (r >> 1);
               const double sg = (r & 1) ? -1.0 : 1.0;
-              double tau = 0.0;
-              row(ws.lP + o, LP(Dm::R_V + r, o), gz[r], sg * da[c], (mode >= 3) ? sg * dz[c] : 0.0, tau);
-              if (mode == 2) bt[c] += sg * tau;
+              double ta = 0.0, tb = 0.0;
+              row(ws.s.lP[o], gz[r], sg * da[c], P ? 0.0 : sg * dz[c], ta, tb, DLR(Dm::R_V + r));
+              if (P) { bta[c] += sg * ta; btb[c] += sg * tb; }
             }
           } else {
             const size_t o = (size_t)Dm::R_V * K + k;
             double n2 = 0.0, uda = 0.0, udz = 0.0;
 #pragma unroll
             for (int j = 0; j < NU; ++j) { n2 += w[NX + j] * w[NX + j]; uda += w[NX + j] * da[NX + j]; udz += w[NX + j] * dz[NX + j]; }
-            double tau = 0.0;
-            row(ws.lP + o, LP(Dm::R_V, o), 0.5 * (n2 - sc.v_max * sc.v_max), uda, (mode >= 3) ? udz : 0.0, tau, ws.sB + k);
-            if (mode == 2) {
+            double ta = 0.0, tb = 0.0;
+            row(ws.s.lP[o], 0.5 * (n2 - sc.v_max * sc.v_max), uda, P ? 0.0 : udz, ta, tb, DLR(Dm::R_V), ws.s.sB + k, &dsb);
+            if (P) {
 #pragma unroll
-              for (int j = 0; j < NU; ++j) bt[NX + j] += tau * w[NX + j];
+              for (int j = 0; j < NU; ++j) { bta[NX + j] += ta * w[NX + j]; btb[NX + j] += tb * w[NX + j]; }
             }
           }
           auto hinge_body = [&](int h, const HingeData<D>& hd) {
@@ -1483,74 +1523,64 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
             const size_t o = (size_t)h * K + k;
             const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
             const double viol = hd.b - ap;
-            const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S), r1 = 0.0, r2 = 0.0;
+            const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S);
             const double rs1 = rcp_fast(s1), rs2 = rcp_fast(s2);
             const double w1 = l1 * rs1, w2 = l2 * rs2, rw = rcp_fast(w1 + w2);
-            // affine step of this hinge pair (sigmu = 0, c = 0)
-            const double t1a = w1 * r1, t2a = w2 * r2;
-            const double rxa = -hw + t1a + t2a;
-            const double dxia = (rxa - w1 * ada) * rw;
-            const double ds1a = -r1 + ada + dxia, ds2a = -r2 + dxia;
+            // affine step of this hinge pair (sigma mu = 0, no second-order term; both primal residuals are zero by construction)
+            const double dxia = (-hw - w1 * ada) * rw;
+            const double ds1a = ada + dxia, ds2a = dxia;
             const double dl1a = -l1 - w1 * ds1a, dl2a = -l2 - w2 * ds2a;
-            if (mode == 1) {
-              qp = fmax(qp, fmax(-ds1a * rs1, -ds2a * rs2)); upd_d(dl1a, l1); upd_d(dl2a, l2);
-              pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += ds1a * dl1a + ds2a * dl2a;
-              return;
-            }
             const double c1 = ds1a * dl1a, c2 = ds2a * dl2a;
-            const double t1 = (sigmu - c1 + l1 * r1) * rs1, t2 = (sigmu - c2 + l2 * r2) * rs2;
-            const double rhs_xi = -hw + t1 + t2;
-            if (mode == 2) {
-              const double th = t1 - w1 * rhs_xi * rw;
+            if (P) {
+              qp = fmax(qp, fmax(-ds1a * rs1, -ds2a * rs2)); upd_d(dl1a, l1); upd_d(dl2a, l2);
+              pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += c1 + c2;
+              // t1 = (sigma mu - c1) / s1, t2 = (sigma mu - c2) / s2; rhs_xi = -hw + t1 + t2; th = t1 - w1 rhs_xi / (w1 + w2)
+              const double t1b = -c1 * rs1, t2b = -c2 * rs2;
+              const double tha = rs1 - w1 * (rs1 + rs2) * rw, thb = t1b - w1 * (-hw + t1b + t2b) * rw;
 #pragma unroll
-              for (int c = 0; c < D; ++c) bt[c] -= av[c] * th;
+              for (int c = 0; c < D; ++c) { bta[c] -= av[c] * tha; btb[c] -= av[c] * thb; }
               return;
             }
+            const double t1 = (sigmu - c1) * rs1, t2 = (sigmu - c2) * rs2;
+            const double rhs_xi = -hw + t1 + t2;
             const double dxi = (rhs_xi - w1 * adz) * rw;
-            const double ds1 = -r1 + adz + dxi, ds2 = -r2 + dxi;
+            const double ds1 = adz + dxi, ds2 = dxi;
             const double dl1 = -l1 + (sigmu - c1) * rs1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) * rs2 - w2 * ds2;
-            if (mode == 3) {
-              qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
-              return;
-            }
-            ws.xi[o] = xi + al_p * dxi;
-            ws.l1[o] = l1 + al_d * dl1; ws.l2[o] = l2 + al_d * dl2;
+            qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
+            st_na(ws.dxi + o, dxi); st_na(ws.dl1 + o, dl1); st_na(ws.dl2 + o, dl2);
           };
           for (int h0 = 0; h0 < NH; h0 += HINGE_CHUNK) {
             HingeData<D> hb[HINGE_CHUNK];
 #pragma unroll
-            for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k);
+            for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k, ws.s);
 #pragma unroll
             for (int c = 0; c < HINGE_CHUNK; ++c)
               if (hb[c].on) hinge_body(h0 + c, hb[c]);
           }
         }
-        if (mode == 2) {
+        if (P) {
+          // gradient of the smooth cost terms: independent of sigma mu
 #pragma unroll
           for (int c = 0; c < D; ++c) {
             const double ql = qlin ? qlin[(size_t)c * K + k] * sc.cs : 0.0;
-            bt[c] += sc.qrho * w[c] + ql;
+            btb[c] += sc.qrho * w[c] + ql;
           }
           if (game) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
               double g, cv, ob;
               game_terms(k, i, w, g, cv, ob);
-              bt[i] += g;
+              btb[i] += g;
             }
           }
-          // stash own-stage rhs piece; interval pieces are added after the barrier (dW is free: the affine
-          // direction lives in dWa)
-#pragma unroll
-          for (int i = 0; i < NS; ++i) dW[k * NSP + i] = bt[i];
         }
       }
-      PHASE(8 + 2 * (mode - 1));
-      // ---- mode epilogues
+      PHASE(8 + 4 * (PASS - 1) / 2);
+      // ---- pass epilogues
       pr[0] = qp; pr[1] = qdn * rcp_fast(qdd);            // max ratios of this thread's rows
-      if (mode == 1) {
-        const int ops[5] = {2, 2, 0, 0, 0};
-        block_reduce<5>(pr, ops, red);
+      if (P) {
+        const int ops[13] = {2, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        block_reduce<13>(pr, ops, red);
         if (tid == 0) {
           // global rows
           // (step lengths are kept as their reciprocals -- max ratios -- until the very end: two divisions in all)
@@ -1571,37 +1601,14 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           const double comp_aff = comp + ap * s2l + ad * sdl + ap * ad * dd;
           double sg = comp_aff * rcp_fast(comp);
           sg = fmin(fmax(sg, 0.0), 1.0);
-          gl[43] = sg * sg * sg * gl[44];
-        }
-        __syncthreads();
-      } else if (mode == 2) {
-        pr[4] = prg;
-        __syncthreads();
-        for (int k = tid; k < K; k += nthr) {
-          const bool fr = (k > 0 && k < K - 1);
-          if (!fr) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) dW[k * NSP + i] = 0.0;
-            continue;
-          }
-          double acc[NS], t[NS];
-#pragma unroll
-          for (int i = 0; i < NS; ++i) acc[i] = dW[k * NSP + i];
-          JpT<Dm>(JAC + (size_t)k * NJ, ST2 + (size_t)k * Dm::ST2, t);
-#pragma unroll
-          for (int i = 0; i < NS; ++i) acc[i] += t[i];
-          JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ST2 + (size_t)(k - 1) * Dm::ST2, t);
-#pragma unroll
-          for (int i = 0; i < NS; ++i) dW[k * NSP + i] = -(acc[i] + t[i]);
-        }
-        const int ops[8] = {2, 2, 0, 0, 0, 0, 0, 0};
-        block_reduce<8>(pr, ops, red);
-        if (tid == 0) {
-          double bg[4] = {red[4], red[5], red[6], red[7]};
+          const double smu = sg * sg * sg * gl[44];
+          gl[43] = smu;
+          // border part of the corrector's right-hand side
+          double bg[4] = {fma(smu, red[11], red[12]), fma(smu, red[5], red[8]), fma(smu, red[6], red[9]), fma(smu, red[7], red[10])};
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r];
-            const double tau = (sigmu - gl[53 + r] + l * rp) * rcp_fast(s);
+            const double tau = (smu - gl[53 + r] + l * rp) * rcp_fast(s);
 #pragma unroll
             for (int i = 0; i < 4; ++i) bg[i] += gG(r, i) * tau;
           }
@@ -1609,6 +1616,30 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           if (fix_sig) bg[0] = 0.0;
 #pragma unroll
           for (int c = 0; c < 4; ++c) gl[34 + c] = -bg[c];
+        }
+        __syncthreads();
+        // own-stage + interval pieces of the corrector's right-hand side, now that sigma mu is known
+        {
+          const double smu = gl[43];
+          for (int k = tid; k < K; k += nthr) {
+            const bool fr = (k > 0 && k < K - 1);
+            if (!fr) continue;
+            double ek[NX], ekm[NX], t[NS], t2[NS];
+            const double* s0 = ST2 + (size_t)k * Dm::ST2;
+            const double* s1 = ST2 + (size_t)(k - 1) * Dm::ST2;
+#pragma unroll
+            for (int i = 0; i < NX; ++i) { ek[i] = fma(smu, s0[i], dW[k * NSP + i]); ekm[i] = fma(smu, s1[i], dW[(k - 1) * NSP + i]); }
+            JpT<Dm>(JAC + (size_t)k * NJ, ek, t);
+            JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ekm, t2);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) btb[i] = -(fma(smu, bta[i], btb[i]) + t[i] + t2[i]);
+          }
+          __syncthreads();            // every thread has read its neighbour's staging out of dW
+          for (int k = tid; k < K; k += nthr) {
+            const bool fr = (k > 0 && k < K - 1);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) dW[k * NSP + i] = fr ? btb[i] : 0.0;
+          }
         }
         __syncthreads();
         // corrector solve (all threads): rg = bg - Y'b ; v = T^-1 b ; dg = S^-1 rg ; dW = v - Y dg
@@ -1647,7 +1678,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           }
         }
         __syncthreads();
-      } else if (mode == 3) {
+      } else {
         // a non-finite direction must never be applied: the iterate stays at the last good (primal feasible) point
         double bad = 0.0;
         for (int k = tid; k < K; k += nthr)
@@ -1660,40 +1691,53 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           double qpm = fmax(red[0], 1.0), qdm = fmax(red[1], 1.0);
           const bool nan_step = red[2] > 0.0 || !isfinite(red[0]) || !isfinite(red[1]) || !isfinite(gd0 + gd1 + gd2 + gd3);
           gl[40] = nan_step ? 2.0 : 0.0;
+          double dsg[3], dlg[3];
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r], rs = rcp_fast(s), wgt = l * rs;
             const double gdz = gG(r, 0) * gd0 + gG(r, 2) * gd2 + gG(r, 3) * gd3;
             const double ds = -rp - gdz, dl = -l + (sigmu - gl[53 + r]) * rs - wgt * ds;
             qpm = fmax(qpm, -ds * rs); qdm = fmax(qdm, -dl * rcp_fast(fmax(l, 1e-290)));
-            gl[56 + r] = ds; gl[59 + r] = dl;
+            dsg[r] = ds; dlg[r] = dl;
           }
           double ap = 1.0 / qpm, ad = 1.0 / qdm;
           if (coupled) { ap = ad = fmin(ap, ad); }
-          gl[41] = fmin(1.0, 0.999 * ap); gl[42] = fmin(1.0, 0.999 * ad);
+          ap = fmin(1.0, 0.999 * ap); ad = fmin(1.0, 0.999 * ad);
+          gl[41] = ap; gl[42] = ad;
+          if (!nan_step) {
+            // the globals move now; the stage variables below; the row state in the next residual pass
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gl[c] += ap * gl[8 + c];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { gl[12 + r] += ap * dsg[r]; gl[15 + r] += ad * dlg[r]; }
+          }
         }
         __syncthreads();
-        if ((int)gl[40] == 2) return false;     // uniform: leave before mode 4 applies anything
-      } else if (mode == 4) {
-        __syncthreads();
-        const double ap = gl[41], ad = gl[42];
-        for (int k = tid; k < K; k += nthr)
+        if ((int)gl[40] == 2) return false;     // uniform: leave before anything is applied
+        {
+          const double ap = gl[41], ad = gl[42];
+          for (int k = tid; k < K; k += nthr) {
+            const bool fr = (k > 0 && k < K - 1);
 #pragma unroll
-          for (int i = 0; i < NS; ++i) W[k * NSP + i] += ap * dW[k * NSP + i];
-        if (tid == 0) {
+            for (int i = 0; i < NS; ++i) W[k * NSP + i] += ap * dW[k * NSP + i];
+            // multipliers of this stage's plain rows, in place (the same rows the passes visit)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) gl[c] += ap * gl[8 + c];
-#pragma unroll
-          for (int r = 0; r < 3; ++r) { gl[12 + r] += ap * gl[56 + r]; gl[15 + r] += ad * gl[59 + r]; }
+            for (int r = 0; r < NPLAIN; ++r) {
+              const bool visited = (r < NEX) ? (k < K - 1) : ((r < Dm::R_P) ? true : fr);
+              if (visited) {
+                const size_t o = (size_t)r * K + k;
+                st_na(ws.s.lP + o, fma(ad, DLR(r), ws.s.lP[o]));
+              }
+            }
+            if (BALL && fr) st_na(ws.s.sB + k, fma(ap, dsb, ws.s.sB[k]));
+          }
         }
         __syncthreads();
       }
-      PHASE(9 + 2 * (mode - 1));
+      PHASE(9 + 4 * (PASS - 1) / 2);
       return true;
     };
-    if (run_mode(std::integral_constant<int, 1>{}) && run_mode(std::integral_constant<int, 2>{}) &&
-        run_mode(std::integral_constant<int, 3>{}))
-      run_mode(std::integral_constant<int, 4>{});
+    if (run_pass(std::integral_constant<int, 1>{})) run_pass(std::integral_constant<int, 3>{});
     if ((int)gl[40] == 2) { status = SCVX_ST_NUMERICAL; break; }   // non-finite step refused (iterate untouched)
   }
 
@@ -1777,7 +1821,7 @@ bool solver_jac_in_smem(int K) {
 template <class M>
 size_t solver_ws_doubles_per_agent(int K, int NH) {
   using Dm = Dims<M>;
-  return (size_t)K * (Dm::NPLAIN + 3 * (size_t)NH + (Dm::BALL ? 1 : 0));
+  return (size_t)K * (Dm::NPLAIN + 6 * (size_t)NH + (Dm::BALL ? 1 : 0));     // row state + the hinge pairs' pending step
 }
 template <class M>
 size_t solver_ws_total_doubles(int n_agents, int K, int NH) {
@@ -1801,6 +1845,10 @@ int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
   int threads = ((a.K + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > SOLVER_MAX_THREADS) threads = SOLVER_MAX_THREADS;
+  if (a.K > threads) {        // the passes keep per-stage partial results in registers across block reductions: one stage per thread
+    snprintf(g_last_error, sizeof(g_last_error), "K=%d exceeds the %d threads of an agent's block", a.K, threads);
+    return SCVX_E_UNSUPPORTED;
+  }
   const size_t jac_off = solver_ws_doubles_per_agent<M>(a.K, a.M + a.n_nbr) * (size_t)a.n_agents;
   if (jac_smem) ipm_kernel<M, true><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
   else ipm_kernel<M, false><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);

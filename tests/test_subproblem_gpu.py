@@ -131,8 +131,8 @@ def test_bad_args_and_workspace(cuda):
     from scvx_b200 import _device, _lib
     lib = _lib.load()
     assert lib.scvx_solve_batched(None, None) == -1
-    assert lib.scvx_solve_workspace_bytes(0, 4, 50, 3, 0) == 4 * 50 * 8 * (28 + 3 * 3)
-    assert lib.scvx_solve_workspace_bytes(1, 1, 10, 2, 3) == 10 * 8 * (31 + 3 * 5 + 1)
+    assert lib.scvx_solve_workspace_bytes(0, 4, 50, 3, 0) == 4 * 50 * 8 * (28 + 6 * 3)      # row state + the hinge pairs' pending step
+    assert lib.scvx_solve_workspace_bytes(1, 1, 10, 2, 3) == 10 * 8 * (31 + 6 * 5 + 1)
     assert lib.scvx_solve_workspace_bytes(9, 1, 10, 0, 0) == 0
     m = omodels.unicycle()
     X, U = m.initialize_trajectory(10)
@@ -224,8 +224,8 @@ def test_long_horizons_K200_and_K220(cuda):
     Jacobians move to the global workspace (same code path otherwise; 256 threads per agent, strided over stages)."""
     from scvx_b200 import _lib
     lib = _lib.load()
-    assert lib.scvx_solve_workspace_bytes(0, 1, 200, 4, 0) == 200 * 8 * (28 + 3 * 4)
-    assert lib.scvx_solve_workspace_bytes(0, 1, 220, 4, 0) == 220 * 8 * (28 + 3 * 4 + 27)     # + K*NJ for the Jacobians
+    assert lib.scvx_solve_workspace_bytes(0, 1, 200, 4, 0) == 200 * 8 * (28 + 6 * 4)
+    assert lib.scvx_solve_workspace_bytes(0, 1, 220, 4, 0) == 220 * 8 * (28 + 6 * 4 + 27)     # + K*NJ for the Jacobians
     rng = np.random.default_rng(5)
     om = helpers.random_unicycle_scene(rng, 4)
     for K in (200, 220):

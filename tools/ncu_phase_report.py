@@ -29,9 +29,9 @@ def phases(src):
     marks = []
     pats = [("cr_factor", r"void cr_factor\("), ("cr_forward", r"void cr_forward\("), ("cr_backward", r"void cr_backward\("),
             ("schur_solve", r"void schur_solve\("), ("assemble_rows", r"void assemble_rows\("), ("kernel_setup", r"^ipm_kernel\("),
-            ("mode0_rows", r"-+ MODE 0$"), ("mode0_assembly_term", r"second half of the assembly"),
-            ("factor_predictor_glue", r"factor \+ predictor solve"), ("modes1-4_rows", r"-+ MODE 1/2/3/4"),
-            ("mode_epilogues", r"---- mode epilogues"), ("epilogue", r"---- epilogue: outputs"), ("host", r"constexpr size_t SMEM_LIMIT"),
+            ("passR_rows", r"-+ RESIDUAL PASS"), ("passR_assembly_term", r"second half of the assembly"),
+            ("factor_predictor_glue", r"factor \+ predictor solve"), ("passPS_rows", r"-+ PASS P / PASS S"),
+            ("pass_epilogues", r"---- pass epilogues"), ("epilogue", r"---- epilogue: outputs"), ("host", r"constexpr size_t SMEM_LIMIT"),
             ("helpers", r"^#include \"common.cuh\""), ("chol/apply", r"void chol_inverse\(")]
     for name, p in pats:
         for i, l in enumerate(L):

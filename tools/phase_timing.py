@@ -25,9 +25,9 @@ torch.cuda.synchronize()
 print(f"{iters} outer iterations of {n} agents: {t0.elapsed_time(t1):.2f} ms; mean IPM iterations {out['ipm_iters'].double().mean(dim=1).tolist()}; optimal {(out['status'] == 0).double().mean().item():.6f}")
 lib.scvx_debug_phase_cycles(buf, 1)
 its = int(out["ipm_iters"][:, 0].sum().item())
-names = {0: "setup", 1: "mode0 rows", 2: "assembly+reduce+term", 3: "cr_factor", 4: "cr_forward<5>", 5: "schur glue", 6: "cr_backward<5>",
-         7: "dWa", 8: "mode1 rows", 9: "mode1 epi", 10: "mode2 rows", 18: "mode2 post+reduce+yb", 16: "cr_forward<1>", 17: "cr_backward<1>",
-         11: "mode2 final dW", 12: "mode3 rows", 13: "mode3 epi", 14: "mode4 rows", 15: "mode4 epi", 19: "epilogue"}
+names = {0: "setup", 1: "pass R rows (+ pending step)", 2: "assembly+reduce+term", 3: "cr_factor", 4: "cr_forward<5>", 5: "schur glue",
+         6: "cr_backward<5>", 7: "dWa", 8: "pass P rows", 18: "pass P reduce+tail+rhs+yb", 16: "cr_forward<1>", 17: "cr_backward<1>",
+         9: "corrector dW", 12: "pass S rows", 13: "pass S tail + W update", 19: "epilogue"}
 tot = sum(buf)
 print(f"agent 0: {its} IPM iterations over {iters} launches; total {tot} cycles; {tot / max(its, 1):.0f} cycles / IPM iteration")
 for i in sorted(names, key=lambda i: -buf[i]):
