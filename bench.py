@@ -18,6 +18,12 @@ value  = agent-iterations/s, iterates resident in HBM, CUDA-event time of the K 
          between steps -- the pass the roofline of ipm_kernel is measured on (the kernel runs alone on its stream there).
 e2e    = same metric through the host-buffer API (PipelinedSCvx.run_host): every step of every lane copies its slice of the
          iterate from pinned host memory to the device, runs, and copies the new iterate + metrics back.
+configs = the other BASELINE configs, each with its own CUDA-event timing (max over ranks), in the same JSON line:
+         config1 (shipped single agent, K=50: ms per outer iteration and per trajectory), config3 / config4 / config5 (coupled
+         agents: ADMM rounds through BatchedADMM, agents SHARDED over the N ranks with one NCCL all-gather per round inside the
+         timed region -- strong scaling: ms per round, all-gather bytes and device time).
+per_rank_ms / weak_scaling_control: the headline's time on every rank, and (N > 1) the same pass with IDENTICAL scenes on
+         every rank, which separates "some rank drew harder scenes" from "ranks slow each other down".
 """
 import argparse
 import ctypes
@@ -46,20 +52,52 @@ def make_scenes(n, seed):
 
 
 # ------------------------------------------------------------------------------------------------ reference arm
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")          # unmodified copy of the reference package (baseline/install_reference.py)
+
+
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "SCvx"))
+
+
 def _ref_agent_iteration(args):
-    """One agent, `n_it` outer iterations of the reference's path restated by the oracle: odeint FOH at default
-    tolerances (first_order_hold.py:52-87) + obstacle linearisation + exact LP (HiGHS in place of cvxpy+ECOS)."""
-    om, K, n_it = args
-    from oracle import foh as ofoh, subproblem as ospb
-    F = ofoh.OracleFOH(om, K)
-    X, U = om.initialize_trajectory(K)
+    """One agent, `n_it` outer iterations of the reference's CPU path.  Stages 1-2 are the REFERENCE'S OWN CODE when its package
+    is present under baseline/_ref (FirstOrderHold.calculate_discretization, first_order_hold.py:52-87, with the model's sympy
+    lambdas; imported through the inert cvxpy stub) and the oracle's restatement of them otherwise; stage 3 is the exact LP
+    (HiGHS) restating SCProblem -- cvxpy/ECOS are absent from the image."""
+    om, K, n_it, use_ref = args
+    from oracle import subproblem as ospb
+    if use_ref:
+        os.environ["SCVX_REFERENCE_ROOT"] = REF_DIR
+        from oracle import refshim
+        if refshim.REFERENCE_ROOT != REF_DIR:
+            refshim.REFERENCE_ROOT = REF_DIR
+        if "SCvx.discretization.first_order_hold" not in sys.modules or sys.modules["SCvx.global_parameters"].K != K:
+            refshim.load(K)
+        from SCvx.discretization.first_order_hold import FirstOrderHold
+        from SCvx.models.unicycle_model import UnicycleModel
+        rm = UnicycleModel(r_init=om.x_init.copy(), r_final=om.x_final.copy(), obstacles=[(list(c), r) for c, r in om.obstacles])
+        F = FirstOrderHold(rm, K)
+        X, U = rm.initialize_trajectory(np.zeros((3, K)), np.zeros((2, K)))
+        disc = lambda X, U, sig: tuple(np.array(m) for m in F.calculate_discretization(X, U, sig))      # noqa: E731
+    else:
+        from oracle import foh as ofoh
+        F = ofoh.OracleFOH(om, K)
+        X, U = om.initialize_trajectory(K)
+        disc = F.calculate_discretization
     sig, tr = 1.0, 100.0
     for _ in range(n_it):
-        mats = F.calculate_discretization(X, U, sig)
+        mats = disc(X, U, sig)
         p = ospb.Params(om, K, mats, X, U, sig, tr)
         r = ospb.solve(p)
         X, U, sig, tr = r["X"], r["U"], r["sigma"], 50.0
     return n_it
+
+
+def _reference_kind():
+    use_ref = reference_available()
+    what = ("stages 1-2 by the reference's own FirstOrderHold + model lambdas (unmodified package under baseline/_ref)" if use_ref
+            else "stages 1-2 by the oracle port (baseline/_ref absent)")
+    return use_ref, ("reference" if use_ref else "port"), what + "; stage 3 by the exact HiGHS LP in place of cvxpy+ECOS (absent from the image)"
 
 
 def run_reference(args, rank):
@@ -67,29 +105,34 @@ def run_reference(args, rank):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
+    use_ref, kind, what = _reference_kind()
     scenes = make_scenes(cores * (args.steps + args.warmup), 0)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         idx = 0
         n_it = 4          # outer iterations per agent per step: the first is atypically cheap (idle dynamics), later ones are not
         for _ in range(args.warmup):
-            pool.map(_ref_agent_iteration, [(scenes[idx + i], K_NODES, n_it) for i in range(cores)]); idx += cores
+            pool.map(_ref_agent_iteration, [(scenes[idx + i], K_NODES, n_it, use_ref) for i in range(cores)]); idx += cores
         t0 = time.perf_counter()
         done = 0
         for _ in range(args.steps):
-            done += sum(pool.map(_ref_agent_iteration, [(scenes[idx + i], K_NODES, n_it) for i in range(cores)])); idx += cores
+            done += sum(pool.map(_ref_agent_iteration, [(scenes[idx + i], K_NODES, n_it, use_ref) for i in range(cores)])); idx += cores
         dt = time.perf_counter() - t0
     val = done / dt
-    sample = (f"{cores} agents (one process per core) x {n_it} outer iterations per step, {args.steps} steps of config 2; "
-              "numpy/scipy odeint FOH at the reference's tolerances + exact HiGHS LP in place of cvxpy+ECOS")
+    sample = (f"A SAMPLE of config 2, not the whole batch: {cores} agents (one process per core) x outer iterations 0-{n_it - 1} from the "
+              f"cold straight-line start per step, {args.steps} steps ({done} agent-iterations in all; the CUDA arm times iterations "
+              f"{max(args.warmup, 3)}.. of all 1024 agents; iteration 0 has idle dynamics and is the cheapest for LSODA, which flatters the "
+              f"CPU); {what}")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": f"{cores} agents x {n_it} cold-start outer iterations per step (see cpu_baseline.sample)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is pure Python (no compiled sources); cvxpy/ECOS absent from the image, so stage 3 is the HiGHS "
-                "restatement, which is FASTER than cvxpy+ECOS (flatters the CPU).  Published anchor: 2.27 agent-iterations/s.",
+        "note": "the reference is pure Python (no compiled sources, no setup.py: `pip install` refuses it, baseline/install_reference.py "
+                "copies the package); cvxpy/ECOS are absent on both boxes (profiles/r02_probe_solvers_gpu_box.json), so stage 3 is the "
+                "HiGHS restatement, which is FASTER than cvxpy+ECOS (flatters the CPU).  Published anchor: 2.27 agent-iterations/s.",
     }))
 
 
@@ -135,7 +178,6 @@ def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from scvx_b200 import _lib
     from scvx_b200.batch import BatchedSCvx, PipelinedSCvx
-    from scvx_b200.models.unicycle_model import UnicycleModel
 
     lanes = int(os.environ.get("SCVX_BENCH_LANES", "4"))
     torch.cuda.set_device(local_rank)
@@ -144,8 +186,8 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     steps, warm = args.steps, max(args.warmup, 3)
-    scenes = make_scenes(N_AGENTS, rank)             # rank r gets its own 1024 scenes (weak scaling)
-    models = [UnicycleModel(r_init=o.x_init, r_final=o.x_final, obstacles=[(list(c), r) for c, r in o.obstacles]) for o in scenes]
+    import bench_configs as cfg
+    models, _ = cfg.config2_models(N_AGENTS, rank)   # rank r gets its own 1024 scenes (weak scaling); seed = rank
     F64 = torch.float64
     flush_buf = torch.empty(64 * 1024 * 1024, dtype=F64, device=dev)       # 512 MB > 126 MB L2
     stream = torch.cuda.current_stream()
@@ -196,7 +238,7 @@ def run_ours(args, rank, world, local_rank):
                 "sigma_sum": float(host["sigma"].sum().item()) if host_api else float(sig.sum().item()),
                 "status_ok": float((stat == 0).double().mean().item()), "eng": eng, "n": n}
 
-    def run_pipelined(host_api):
+    def run_pipelined(host_api, models=models):
         """The K timed steps through PipelinedSCvx (lanes on their own streams), one CUDA-event pair around all of them."""
         P = PipelinedSCvx(models, K_NODES, n_lanes=lanes, max_iter=warm + steps).start()
         host = None
@@ -232,6 +274,87 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         return {"ms": a.elapsed_time(b_), "n_outer": int(out["n_outer"]), "converged": float((out["active"] == 0).double().mean().item())}
 
+    def allmax(x):
+        t = torch.tensor([x], dtype=F64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allranks(x):
+        t = torch.tensor([x], dtype=F64, device=dev)
+        if world == 1:
+            return [float(x)]
+        out = torch.empty(world, dtype=F64, device=dev)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().tolist()
+
+    def run_config1():
+        """BASELINE config 1: the shipped single agent, K=50 -- a LATENCY number (one block on one SM).  Rank 0 only."""
+        model, K1 = cfg.config1_model()
+        eng = BatchedSCvx([model], K1, max_iter=30)
+        eng.solve(early_exit=False)                          # warm-up: a whole trajectory
+        torch.cuda.synchronize()
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        out = eng.solve(early_exit=False)
+        b_.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b_)
+        # the reference-facing call: SCVXSolver(model).solve() (host arrays in and out, log records built on the host)
+        from scvx_b200.optimization.scvx_solver import SCVXSolver
+        sv = SCVXSolver(model, K1)
+        t0 = time.perf_counter(); Xs, Us, sg, lg = sv.solve(); wall = time.perf_counter() - t0
+        m = out["metrics"][-1, 0].cpu().tolist()
+        return {"workload": "config1: shipped unicycle (start (-8,-8,0), goal (8,8,0), 3 discs), K=50, 30 outer iterations, one agent",
+                "ms_per_trajectory": ms, "ms_per_outer_iteration": ms / 30, "outer_iterations": 30,
+                "mean_ipm_iterations": float(out["ipm_iters"].double().mean().item()),
+                "scvxsolver_solve_wall_ms": 1e3 * wall, "scvxsolver_outer_iterations": len(lg.records),
+                "final": {"nu_norm": m[0], "slack": m[1], "sigma": m[5],
+                          "subproblem_value": float(out["objective"][-1, 0].item()), "all_optimal": bool((out["status"] == 0).all().item())},
+                "note": "device time of BatchedSCvx on a batch of one (no host sync inside the loop); the outer loop does not converge "
+                        "in 30 iterations in the reference either (its trust region never shrinks, scvx_solver.py:125-133); "
+                        "profiles/r02_config1_end_to_end.md has the per-iteration table against the exact LP"}
+
+    def run_admm(c, rounds):
+        """A coupled config: `rounds` ADMM rounds through BatchedADMM, agents sharded over the ranks, ONE all-gather per round
+        inside the timed region (NCCL for N > 1; none at N = 1)."""
+        from scvx_b200.batch import BatchedADMM
+        ms_models, K_ = c["models"], c["K"]
+        eng = BatchedADMM(ms_models, c["d_min"], K_, rho_admm=1.0, max_iter=1, si_variant=c["si"], **c["kw"])
+        XU = [m.initialize_trajectory(np.zeros((3, K_)), np.zeros((m.n_u, K_))) for m in ms_models]
+        X0 = torch.as_tensor(np.stack([x for x, _ in XU])).to(dev); U0 = torch.as_tensor(np.stack([u for _, u in XU])).to(dev)
+        eng.solve(X0, U0, c["sigma"])                        # warm-up round (allocations, NCCL channels)
+        eng.max_iter = rounds
+        eng.profile = True
+        barrier()
+        l0 = eng.launches
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        out = eng.solve(X0, U0, c["sigma"])
+        b_.record(stream)
+        barrier()
+        ms = a.elapsed_time(b_)
+        g_ms, g_n = eng.allgather_ms()
+        ok = torch.tensor([float((eng.ws.status == 0).sum().item()) if eng.nl else 0.0], dtype=F64, device=dev)
+        if world > 1:
+            dist.all_reduce(ok)
+        ms_all = allmax(ms)
+        N = len(ms_models)
+        P = out["X"][:, :c["d"], :]
+        sep = None
+        if N <= 512:
+            dd = ((P[:, None] - P[None]) ** 2).sum(dim=2).sqrt() + torch.eye(N, device=dev, dtype=F64)[:, :, None] * 1e9
+            sep = float(dd.min().item())
+        import hashlib
+        return {"workload": c["name"], "agents": N, "agents_per_rank": eng.per, "rounds": rounds, "ms_per_round": ms_all / rounds,
+                "per_rank_ms_per_round": [v / rounds for v in allranks(ms)],
+                "agent_iterations_per_sec": N * rounds / (ms_all * 1e-3),
+                "allgather_bytes_per_round": eng.allgather_bytes, "allgather_ms_per_round": allmax(g_ms) / max(g_n, 1),
+                "collective": "none (one rank)" if world == 1 else "torch.distributed.all_gather_into_tensor (NCCL), inside the timed region",
+                "gpu_launches_per_round": (eng.launches - l0) / rounds, "optimal_frac_last_round": float(ok.item()) / N,
+                "primal_residual": [round(v, 6) for v in out["primal_hist"]], "min_separation": sep,
+                "sha1_X": hashlib.sha1(np.ascontiguousarray(out["X"].cpu().numpy()).tobytes()).hexdigest()[:16]}
+
     with ClockSampler(local_rank) as clk:
         r_dev = run(False)                 # synchronous steps: roofline pass
         r_e2e_sync = run(True)
@@ -239,13 +362,25 @@ def run_ours(args, rank, world, local_rank):
         r_e2e = run_pipelined(True)        # the measured e2e
         r_traj = run_trajectories()
     clocks = clk.summary()
+    # weak-scaling control: the same pass with IDENTICAL scenes (seed 0) on every rank
+    r_ctrl = run_pipelined(False, cfg.config2_models(N_AGENTS, 0)[0]) if world > 1 else None
+    skip = set(os.environ.get("SCVX_BENCH_SKIP", "").split(","))
+    configs = {}
+    if "config1" not in skip:
+        c1 = run_config1() if rank == 0 else None
+        barrier()
+        configs["config1"] = c1
+    for name, maker, rounds in (("config3", cfg.config3_models, 10), ("config4", cfg.config4_models, 5), ("config5", cfg.config5_models, 3)):
+        if name not in skip:
+            configs[name] = run_admm(maker(), rounds)
 
-    def allmax(x):
-        t = torch.tensor([x], dtype=F64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    per_rank_ms = allranks(r_pipe["ms"] / steps)
+    ctrl = None
+    if r_ctrl is not None:
+        ctrl_ranks = allranks(r_ctrl["ms"] / steps)
+        ctrl = {"per_rank_ms_per_step": ctrl_ranks, "ms_per_step": max(ctrl_ranks),
+                "note": "same pass, IDENTICAL scenes (seed 0) on every rank: what is left of the gap to N=1 here is ranks slowing each other "
+                        "down (host launch contention, shared power/clock budget); the rest of the headline's gap is the unluckiest rank's scenes"}
     ms = allmax(r_pipe["ms"]); ms_e2e = allmax(r_e2e["ms"]); ms_traj = allmax(r_traj["ms"])
     ms_sync = allmax(r_dev["ms"]); ms_e2e_sync = allmax(r_e2e_sync["ms"])
     total_units = N_AGENTS * world * steps
@@ -304,6 +439,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": int(r_pipe["launches"]),
+            "per_rank_ms_per_step": per_rank_ms, "weak_scaling_control": ctrl,
+            "configs": configs,
             "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
             "agent_trajectories_per_sec": N_AGENTS * world / (ms_traj * 1e-3),
             "trajectory_run": {"ms": ms_traj, "outer_iterations": r_traj["n_outer"], "converged_frac": r_traj["converged"],
@@ -355,15 +492,15 @@ def cpu_baseline_sample():
     cores = os.cpu_count() or 1
     n_it = 8
     scenes = make_scenes(4 * cores, 12345)
+    use_ref, kind, what = _reference_kind()
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_ref_agent_iteration, [(s, K_NODES, 1) for s in scenes[:cores]])      # warm the workers (imports, HiGHS)
+        pool.map(_ref_agent_iteration, [(s, K_NODES, 1, use_ref) for s in scenes[:cores]])      # warm the workers (imports, HiGHS)
         t0 = time.perf_counter()
-        done = sum(pool.map(_ref_agent_iteration, [(s, K_NODES, n_it) for s in scenes], chunksize=1))
+        done = sum(pool.map(_ref_agent_iteration, [(s, K_NODES, n_it, use_ref) for s in scenes], chunksize=1))
         dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{4 * cores} agents x {n_it} outer iterations of config 2 (odeint FOH at the reference's tolerances + exact HiGHS LP "
-                      f"in place of cvxpy+ECOS), one process per core, {dt:.1f} s wall"}
+    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{4 * cores} agents x outer iterations 0-{n_it - 1} of config 2, one process per core, {dt:.1f} s wall; {what}"}
 
 
 def main():

@@ -455,9 +455,25 @@ class BatchedADMM:
             self.col_a = torch.empty((self.nl, n_slots, b.d, K), dtype=F64, device=dev)
             self.col_b = torch.empty((self.nl, n_slots, K), dtype=F64, device=dev)
         self.launches = 0
+        self.profile = False             # True: CUDA events around the round's all-gather (see allgather_ms)
+        self._gather_events = []
 
     def _gather(self, X_local, U_local):
         return allgather_shards(X_local, U_local, self.N, self.per, self.dist, self.group)
+
+    def allgather_ms(self):
+        """Device time of the all-gathers of the solves since the last call (profile=True), this rank; synchronises."""
+        torch.cuda.synchronize(self.all.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._gather_events)
+        n = len(self._gather_events)
+        self._gather_events = []
+        return ms, n
+
+    @property
+    def allgather_bytes(self):
+        """Bytes every rank RECEIVES per round: the padded (X, U) shards of all ranks."""
+        b = self.all
+        return 0 if self.world == 1 else int(self.world * self.per * (b.n_x + b.n_u) * self.K * 8)
 
     def solve(self, X_refs, U_refs, sigma_ref):
         """X_refs (N, n_x, K), U_refs (N, n_u, K) device tensors (every rank holds all of them).
@@ -532,7 +548,12 @@ class BatchedADMM:
                 X_new, U_new = self.ws.X, self.ws.U
             else:
                 X_new = torch.empty((0, b.n_x, K), dtype=F64, device=dev); U_new = torch.empty((0, b.n_u, K), dtype=F64, device=dev)
+            if self.profile:
+                ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                ev[0].record()
             X_all, U_all = self._gather(X_new, U_new)
+            if self.profile:
+                ev[1].record(); self._gather_events.append(ev)
             X_all, U_all = X_all.clone(), U_all.clone()
             P = X_all[:, :d, :].contiguous()
             pr, du = _device.consensus_update(P, Y, Lam, self.rho)

@@ -82,3 +82,25 @@ def make_problem_sequence(om, K, n_iter, tr0=100.0, **kw):
         tr = min(tr * (1.5 if ev["nu_norm"] < 1e-2 and ev["slack_sum"] < 1e-2 else 1.2), 50.0)
         X, U, sig = r["X"], r["U"], r["sigma"]
     return out
+
+
+def config5_style_problem(rng, K=200, M=32, NB=16, sigma=25.0, d_min=0.5, rho=1.0):
+    """One agent's ADMM sub-problem at BASELINE config-5 size: unicycle, K=200 nodes, M=32 discs drawn from a shared field,
+    NB=16 neighbours (the compact k-nearest-neighbour coupling of BatchedADMM at N=8192)."""
+    from oracle.models import linearize_collision
+    field = [(list(rng.uniform(-7, 7, 2)), float(rng.uniform(0.3, 0.9))) for _ in range(2 * M)]
+    ms = []
+    for _ in range(NB + 1):
+        y0 = rng.uniform(-9, 9)
+        start = np.array([rng.uniform(-9, -8), y0, 0.0]); goal = np.array([-start[0], -y0, 0.0])
+        obs = [o for o in field if min(np.linalg.norm(np.array(o[0]) - start[:2]), np.linalg.norm(np.array(o[0]) - goal[:2])) > o[1] + 1.0]
+        assert len(obs) >= M
+        ms.append(omodels.unicycle(r_init=start, r_final=goal, obstacles=obs[:M]))
+    XU = [m.initialize_trajectory(K) for m in ms]
+    Xs = [x + (0.05 * rng.normal(size=x.shape) if j else 0) for j, (x, _) in enumerate(XU)]
+    mats = ofoh.OracleFOH(ms[0], K).calculate_discretization(Xs[0], XU[0][1], sigma)
+    nbrs = []
+    for j in range(1, NB + 1):
+        a, _ = linearize_collision(2, d_min, Xs[0], Xs[j])
+        nbrs.append({"a": a, "Y": Xs[j][:2] + 0.01 * rng.normal(size=(2, K)), "Lam": 0.1 * rng.normal(size=(2, K))})
+    return ospb.Params(ms[0], K, mats, Xs[0], XU[0][1], sigma, 100.0, neighbors=nbrs, rho=rho, d_min=d_min)

@@ -18,7 +18,10 @@ def _check(line, n_gpus):
     assert d["n_gpus"] == n_gpus and d["steps"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["value"] > 0 and d["dtype"] == "f64" and "workload" in d["config"]
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and cb["sample"]
+    # stages 1-2 run the reference's own package when baseline/_ref holds it (baseline/install_reference.py), else the oracle port
+    has_ref = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "SCvx"))
+    assert cb["kind"] == ("reference" if has_ref else "port") and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"]
+    assert "SAMPLE" in cb["sample"] and "outer iterations 0-3" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

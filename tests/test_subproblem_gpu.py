@@ -102,6 +102,38 @@ def test_admm_variant_qp(cuda, kind, N, K):
         np.testing.assert_allclose(ws.col_slack[i].cpu().numpy(), np.stack(e["S"]), rtol=0, atol=1e-12)
 
 
+def _assert_bracketed(ws, ps, gap_rtol=1e-6):
+    """Every candidate of the batch certified by the exact-LP bracket; the LPs run on host threads (HiGHS releases the GIL:
+    four config-4-size brackets take the wall time of one, ~50 s)."""
+    from concurrent.futures import ThreadPoolExecutor
+    cands = [(p, ws.X[i].cpu().numpy(), ws.U[i].cpu().numpy(), ws.sigma[i].item()) for i, p in enumerate(ps)]
+    assert (ws.status[:len(ps)] == 0).all(), (ws.status.tolist(), ws.iters.tolist())
+    with ThreadPoolExecutor(len(ps)) as pool:
+        out = list(pool.map(lambda c: ospb.qp_bracket(*c), cands))
+    for i, (f0, lb, viol, ok) in enumerate(out):
+        assert ok and viol <= VIOL_TOL, (i, viol)
+        assert 0 <= f0 - lb + 1e-9 * abs(f0) and (f0 - lb) <= gap_rtol * abs(f0), (i, f0, lb)
+
+
+def test_config4_size_single_integrator_admm(cuda):
+    """BASELINE config 4 size: 256 single-integrator agents, K=100, all pairs -> 255 inter-agent rows per stage (25 500 hinge
+    pairs per agent).  Four agents of one ADMM round, each certified by Kelley cuts + the exact-LP bracket."""
+    rng = np.random.default_rng(4)
+    ps = [_admm_problem("single_integrator", 256, 100, i, rng) for i in range(4)]
+    assert all(len(p.neighbors) == 255 for p in ps)
+    ws = helpers.solve_batch_on_gpu(ps, cuda)
+    assert (torch.linalg.norm(ws.U, dim=1) <= 1.0 + 1e-9).all()
+    _assert_bracketed(ws, ps)
+
+
+def test_config5_size_unicycle_admm(cuda):
+    """BASELINE config 5 size: K=200 nodes, M=32 discs, 16 neighbours per agent (48 hinge pairs per stage), unicycle QP."""
+    rng = np.random.default_rng(55)
+    ps = [helpers.config5_style_problem(rng) for _ in range(4)]
+    assert ps[0].K == 200 and len(ps[0].model.obstacles) == 32 and len(ps[0].neighbors) == 16
+    _assert_bracketed(helpers.solve_batch_on_gpu(ps, cuda), ps)
+
+
 def test_edge_cases(cuda):
     """No obstacles; start inside an inflated obstacle (slack > 0 forced at the fixed node and nearby);
     trust region at its 1e-3 floor; the smallest horizon with a free stage (K=3)."""
