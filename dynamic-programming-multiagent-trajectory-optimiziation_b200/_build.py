@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscvx_b200.so")
-SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "lti_qp.cu", "utils.cu", "intersample.cu", "probe.cu"]
+SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "lti_qp.cu", "utils.cu", "intersample.cu", "probe.cu", "user_model.cu"]
 OBJ_DIR = os.path.join(HERE, "build")          # object files (git-ignored); only the .so sits next to the package
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
@@ -47,7 +47,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -12,7 +12,19 @@ from ._lib import SolveArgs, check, load, ptr, stream_ptr
 
 F64 = torch.float64
 
-MODEL_DIMS = {_lib.MODEL_UNICYCLE: (3, 2, 2), _lib.MODEL_SINGLE_INTEGRATOR: (3, 3, 3)}
+
+
+class _ModelDims(dict):
+    """model id -> (n_x, n_u, d); ids of models registered at run time (codegen.register) are looked up in the library."""
+
+    def __missing__(self, model_id):
+        n_x, n_u, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(load().scvx_model_dims(int(model_id), ctypes.byref(n_x), ctypes.byref(n_u), ctypes.byref(d)), "scvx_model_dims")
+        self[model_id] = (n_x.value, n_u.value, d.value)
+        return self[model_id]
+
+
+MODEL_DIMS = _ModelDims({_lib.MODEL_UNICYCLE: (3, 2, 2), _lib.MODEL_SINGLE_INTEGRATOR: (3, 3, 3)})
 
 
 def _dev(t):

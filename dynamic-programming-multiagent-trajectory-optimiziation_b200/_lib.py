@@ -12,6 +12,7 @@ LIB_PATH = os.environ.get("SCVX_LIB") or os.path.join(HERE, "libscvx_b200.so")
 
 MODEL_UNICYCLE = 0
 MODEL_SINGLE_INTEGRATOR = 1
+MODEL_USER_BASE = 16          # ids of models registered at run time (codegen.register)
 
 ST_OPTIMAL, ST_MAXITER, ST_NUMERICAL = 0, 1, 2
 
@@ -57,6 +58,8 @@ SIGNATURES = {
     "scvx_abi_version": (_c_int, []),
     "scvx_last_error": (ctypes.c_char_p, []),
     "scvx_model_dims": (_c_int, [_c_int, ctypes.POINTER(_c_int), ctypes.POINTER(_c_int), ctypes.POINTER(_c_int)]),
+    "scvx_user_model_register": (_c_int, [ctypes.c_char_p, _c_int, _c_int, _c_int, ctypes.c_char_p, ctypes.POINTER(_c_int)]),
+    "scvx_user_model_log": (ctypes.c_char_p, []),
     "scvx_foh_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 8 + [_c_dp]),
     "scvx_integrate_piecewise_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 4 + [_c_dp]),
     "scvx_integrate_full_batched": (_c_int, [_c_int, _c_int, _c_int, _c_int] + [_c_dp] * 4 + [_c_dp]),

@@ -284,6 +284,47 @@ class PipelinedSCvx:
         self._launch_base = launches0
         return self
 
+    def build_lane_graphs(self):
+        """One CUDA graph PER LANE holding one outer iteration of that lane (its 5 launches), replayed on the lane's own stream:
+        the lanes stay independent -- `build_graph` joins all lanes at the end of every replay, which was measured to cost the
+        whole benefit of the lanes (profiles/r02b_graph_lanes.jsonl) -- and the host issues n_lanes graph launches per step
+        instead of 5 x n_lanes kernel launches through Python."""
+        if self.state is None:
+            raise RuntimeError("PipelinedSCvx.build_lane_graphs: call start() first")
+        if any(e._order is None for e in self.engines):
+            self.run(1)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._lmet = [torch.zeros((c - a, 6), dtype=F64, device=self.device) for a, c in self.bounds]
+        self._lgraphs = []
+        launches0 = self.launches
+        for eng, st, lm, (X, U, sig, tr, act, _met) in zip(self.engines, self.streams, self._lmet, self.state):
+            g = torch.cuda.CUDAGraph()
+            st.synchronize()
+            with torch.cuda.graph(g, stream=st):
+                eng.iterate(X, U, sig, tr, act, lm)
+            self._lgraphs.append(g)
+        self._lane_graph_launches = self.launches - launches0
+        for e in self.engines:
+            e.launches = 0
+        self._launch_base = launches0
+        return self
+
+    def run_lane_graphs(self, n_iter, keep_history=True):
+        """n_iter outer iterations of every lane by replaying the lane graphs on the lane streams; the calling stream waits
+        for all lanes at the end (no host synchronisation)."""
+        if self.it + n_iter > self.max_iter:
+            raise ValueError("PipelinedSCvx.run_lane_graphs: more iterations than max_iter")
+        main = self._fork()
+        for k in range(n_iter):
+            for g, st, lm, s_ in zip(self._lgraphs, self.streams, self._lmet, self.state):
+                with torch.cuda.stream(st):
+                    g.replay()
+                    if keep_history:
+                        s_[5][self.it + k].copy_(lm, non_blocking=True)
+            self._launch_base += self._lane_graph_launches
+        self.it += n_iter
+        self._join(main)
+
     def run_graph(self, n_iter, keep_history=True):
         """n_iter outer iterations by graph replay (n_iter must be a multiple of the captured steps_per_graph)."""
         if n_iter % self._gsteps:

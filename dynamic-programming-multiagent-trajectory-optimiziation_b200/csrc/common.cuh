@@ -70,12 +70,27 @@ struct SingleIntegrator {
   }
 };
 
+// models registered at run time (user_model.cu)
+bool user_model_dims(int model_id, int* nx, int* nu, int* d);
+int user_model_launch(int model_id, int which, unsigned blocks, unsigned threads, void** args, cudaStream_t st, const char* where);
+
 inline bool model_dims(int model_id, int* nx, int* nu, int* d) {
   switch (model_id) {
     case SCVX_MODEL_UNICYCLE: *nx = 3; *nu = 2; *d = 2; return true;
     case SCVX_MODEL_SINGLE_INTEGRATOR: *nx = 3; *nu = 3; *d = 3; return true;
-    default: return false;
+    default: return user_model_dims(model_id, nx, nu, d);
   }
+}
+
+// Stages 2-3 depend on a model's dimensions and constraint kind only: a registered model runs through the kernels of the shipped
+// model with its shape.  Returns SCVX_MODEL_UNICYCLE / SCVX_MODEL_SINGLE_INTEGRATOR, or -1 when no kernel of that shape exists.
+inline int solver_shape_of(int model_id) {
+  if (model_id == SCVX_MODEL_UNICYCLE || model_id == SCVX_MODEL_SINGLE_INTEGRATOR) return model_id;
+  int nx, nu, d;
+  if (!user_model_dims(model_id, &nx, &nu, &d)) return -1;
+  if (nx == 3 && nu == 2 && d == 2) return SCVX_MODEL_UNICYCLE;
+  if (nx == 3 && nu == 3 && d == 3) return SCVX_MODEL_SINGLE_INTEGRATOR;
+  return -1;
 }
 
 }  // namespace scvx

@@ -1,308 +1,34 @@
-// foh.cu -- stage 1: first-order-hold discretisation of the augmented ODE, fp64 RK4, sm_100a.
+// foh.cu -- stage 1 entry points: first-order-hold discretisation of the augmented ODE and the nonlinear propagators, fp64 RK4,
+// sm_100a, for the two shipped models (device code: foh_kernels.cuh; user models: user_model.cu compiles the same text with NVRTC).
 //
-// Replaces FirstOrderHold.calculate_discretization / _ode_dVdt
-// (SCvx/discretization/first_order_hold.py:52-125) for a batch of agents.
-//
-// Mapping: ONE THREAD per (agent, interval).  The augmented state V = [x, Phi, B-, B+, S, z] splits
-// into a genuinely dynamic part (x, Phi: NX + NX^2 values) and pure quadratures (B-, B+, S, z) whose
-// derivatives depend only on (t, x, Phi).  Classical RK4 on the full V is therefore identical to RK4
-// on (x, Phi) with the quadrature integrands accumulated at the four stage points with weights
-// h/6, h/3, h/3, h/6 -- which keeps the per-thread live state at ~70 doubles (no spills) instead of
-// 4 x 30.  Global loads/stores are coalesced over k (the fastest index of every array).
+// Replaces FirstOrderHold.calculate_discretization / _ode_dVdt / integrate_nonlinear_* (SCvx/discretization/first_order_hold.py:52-162).
 #include "common.cuh"
+#include "foh_kernels.cuh"
 
 namespace scvx {
 
 thread_local char g_last_error[256] = "";
-
-template <int N>
-__device__ __forceinline__ void inv3(const double (*P)[N], double (*Pi)[N]) {
-  static_assert(N == 3, "closed-form inverse is written for n_x = 3");
-  const double c00 = P[1][1] * P[2][2] - P[1][2] * P[2][1];
-  const double c01 = P[1][2] * P[2][0] - P[1][0] * P[2][2];
-  const double c02 = P[1][0] * P[2][1] - P[1][1] * P[2][0];
-  const double det = P[0][0] * c00 + P[0][1] * c01 + P[0][2] * c02;
-  const double r = 1.0 / det;
-  Pi[0][0] = c00 * r;
-  Pi[1][0] = c01 * r;
-  Pi[2][0] = c02 * r;
-  Pi[0][1] = (P[0][2] * P[2][1] - P[0][1] * P[2][2]) * r;
-  Pi[1][1] = (P[0][0] * P[2][2] - P[0][2] * P[2][0]) * r;
-  Pi[2][1] = (P[0][1] * P[2][0] - P[0][0] * P[2][1]) * r;
-  Pi[0][2] = (P[0][1] * P[1][2] - P[0][2] * P[1][1]) * r;
-  Pi[1][2] = (P[0][2] * P[1][0] - P[0][0] * P[1][2]) * r;
-  Pi[2][2] = (P[0][0] * P[1][1] - P[0][1] * P[1][0]) * r;
-}
-
-// One evaluation of _ode_dVdt (first_order_hold.py:89-125) at time t with state (x, Phi):
-// returns kx = sigma f, kP = A_s Phi and ADDS w * {alpha Phi^-1 B_s, beta Phi^-1 B_s, Phi^-1 f,
-// Phi^-1(-A_s x - B_s u)} into the quadrature accumulators.
-template <class M>
-__device__ __forceinline__ void rhs_stage(double t, double inv_dt, double sigma, const double* u0, const double* du,
-                                          const double* x, const double (*Phi)[M::NX], double* kx,
-                                          double (*kP)[M::NX], double w, double (*Bm)[M::NU], double (*Bp)[M::NU],
-                                          double* S, double* Z) {
-  constexpr int NX = M::NX, NU = M::NU;
-  const double beta = t * inv_dt;        // t / dt
-  const double alpha = 1.0 - beta;       // (dt - t) / dt
-  double u[NU];
-#pragma unroll
-  for (int j = 0; j < NU; ++j) u[j] = u0[j] + beta * du[j];
-  double f[NX], A[NX][NX], B[NX][NU];
-  M::eval(x, u, f, A, B);
-  // A_s = sigma A, B_s = sigma B
-  double zt[NX];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    kx[i] = sigma * f[i];
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      A[i][j] *= sigma;
-      acc -= A[i][j] * x[j];
-    }
-#pragma unroll
-    for (int j = 0; j < NU; ++j) {
-      B[i][j] *= sigma;
-      acc -= B[i][j] * u[j];
-    }
-    zt[i] = acc;   // -A_s x - B_s u
-  }
-#pragma unroll
-  for (int i = 0; i < NX; ++i)
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      double acc = 0.0;
-#pragma unroll
-      for (int l = 0; l < NX; ++l) acc += A[i][l] * Phi[l][j];
-      kP[i][j] = acc;
-    }
-  double Pi[NX][NX];
-  inv3<NX>(Phi, Pi);
-  const double wa = w * alpha, wb = w * beta;
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    double sf = 0.0, sz = 0.0;
-#pragma unroll
-    for (int l = 0; l < NX; ++l) {
-      sf += Pi[i][l] * f[l];
-      sz += Pi[i][l] * zt[l];
-    }
-    S[i] += w * sf;
-    Z[i] += w * sz;
-#pragma unroll
-    for (int j = 0; j < NU; ++j) {
-      double pb = 0.0;
-#pragma unroll
-      for (int l = 0; l < NX; ++l) pb += Pi[i][l] * B[l][j];
-      Bm[i][j] += wa * pb;
-      Bp[i][j] += wb * pb;
-    }
-  }
-}
-
-__device__ __forceinline__ int auto_substeps(double sigma, double dt, const double* u0, const double* u1, int nu) {
-  // Measured on the unicycle (tests/golden, K=50, |u|<=1): the error of B_bar/C_bar relative to their own scale
-  // behaves like 8.6e-3 * lambda^2 / n^4 for small lambda = sigma*dt*max(1,|u|) (first-order-hold ramp of u inside the
-  // interval) and like lambda^5/(28 n^4) for large lambda.  n below puts both at <= ~1.5e-10.
-  double um = 1.0;
-  for (int j = 0; j < nu; ++j) um = fmax(um, fmax(fabs(u0[j]), fabs(u1[j])));
-  const double lam = fabs(sigma) * dt * um;
-  double n = ceil(fmax(100.0 * sqrt(lam), 130.0 * pow(lam, 1.25)));
-  n = fmin(fmax(n, 8.0), 8192.0);
-  return (int)n;
-}
 
 template <class M>
 __global__ void __launch_bounds__(128)
 foh_rk4_kernel(int n_agents, int K, int n_sub, const double* __restrict__ X, const double* __restrict__ U,
                const double* __restrict__ sigma_arr, double* __restrict__ A_bar, double* __restrict__ B_bar,
                double* __restrict__ C_bar, double* __restrict__ S_bar, double* __restrict__ z_bar) {
-  constexpr int NX = M::NX, NU = M::NU;
-  const int Km1 = K - 1;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)n_agents * Km1) return;
-  const int agent = (int)(gid / Km1);
-  const int k = (int)(gid - (long long)agent * Km1);
-  const double sigma = sigma_arr[agent];
-  const double dt = 1.0 / (double)Km1;
-  const double inv_dt = (double)Km1;
-
-  const double* Xa = X + (size_t)agent * NX * K;
-  const double* Ua = U + (size_t)agent * NU * K;
-  double x[NX], u0[NU], du[NU], u1[NU];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) x[i] = Xa[(size_t)i * K + k];
-#pragma unroll
-  for (int j = 0; j < NU; ++j) {
-    u0[j] = Ua[(size_t)j * K + k];
-    u1[j] = Ua[(size_t)j * K + k + 1];
-    du[j] = u1[j] - u0[j];
-  }
-  double Phi[NX][NX], Bm[NX][NU], Bp[NX][NU], S[NX], Z[NX];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    S[i] = 0.0; Z[i] = 0.0;
-#pragma unroll
-    for (int j = 0; j < NX; ++j) Phi[i][j] = (i == j) ? 1.0 : 0.0;
-#pragma unroll
-    for (int j = 0; j < NU; ++j) { Bm[i][j] = 0.0; Bp[i][j] = 0.0; }
-  }
-  const int ns = (n_sub > 0) ? n_sub : auto_substeps(sigma, dt, u0, u1, NU);
-  const double h = dt / (double)ns;
-  const double h2 = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
-
-  for (int s = 0; s < ns; ++s) {
-    const double t = (double)s * h;
-    double kx[NX], kP[NX][NX], ax[NX], aP[NX][NX], xs[NX], Ps[NX][NX];
-    // stage 1
-    rhs_stage<M>(t, inv_dt, sigma, u0, du, x, Phi, kx, kP, h6, Bm, Bp, S, Z);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      ax[i] = kx[i]; xs[i] = x[i] + h2 * kx[i];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) { aP[i][j] = kP[i][j]; Ps[i][j] = Phi[i][j] + h2 * kP[i][j]; }
-    }
-    // stage 2
-    rhs_stage<M>(t + h2, inv_dt, sigma, u0, du, xs, Ps, kx, kP, h3, Bm, Bp, S, Z);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      ax[i] += 2.0 * kx[i]; xs[i] = x[i] + h2 * kx[i];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) { aP[i][j] += 2.0 * kP[i][j]; Ps[i][j] = Phi[i][j] + h2 * kP[i][j]; }
-    }
-    // stage 3
-    rhs_stage<M>(t + h2, inv_dt, sigma, u0, du, xs, Ps, kx, kP, h3, Bm, Bp, S, Z);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      ax[i] += 2.0 * kx[i]; xs[i] = x[i] + h * kx[i];
-#pragma unroll
-      for (int j = 0; j < NX; ++j) { aP[i][j] += 2.0 * kP[i][j]; Ps[i][j] = Phi[i][j] + h * kP[i][j]; }
-    }
-    // stage 4
-    rhs_stage<M>(t + h, inv_dt, sigma, u0, du, xs, Ps, kx, kP, h6, Bm, Bp, S, Z);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      x[i] += h6 * (ax[i] + kx[i]);
-#pragma unroll
-      for (int j = 0; j < NX; ++j) Phi[i][j] += h6 * (aP[i][j] + kP[i][j]);
-    }
-  }
-
-  // epilogue (first_order_hold.py:76-85): A_bar = Phi, B_bar = Phi B-, C_bar = Phi B+, S_bar = Phi S, z_bar = Phi z,
-  // matrices flattened column-major into column k.
-  double* Ao = A_bar + (size_t)agent * NX * NX * Km1 + k;
-  double* Bo = B_bar + (size_t)agent * NX * NU * Km1 + k;
-  double* Co = C_bar + (size_t)agent * NX * NU * Km1 + k;
-  double* So = S_bar + (size_t)agent * NX * Km1 + k;
-  double* Zo = z_bar + (size_t)agent * NX * Km1 + k;
-#pragma unroll
-  for (int j = 0; j < NX; ++j)
-#pragma unroll
-    for (int i = 0; i < NX; ++i) Ao[(size_t)(j * NX + i) * Km1] = Phi[i][j];
-#pragma unroll
-  for (int j = 0; j < NU; ++j)
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      double b = 0.0, c = 0.0;
-#pragma unroll
-      for (int l = 0; l < NX; ++l) { b += Phi[i][l] * Bm[l][j]; c += Phi[i][l] * Bp[l][j]; }
-      Bo[(size_t)(j * NX + i) * Km1] = b;
-      Co[(size_t)(j * NX + i) * Km1] = c;
-    }
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    double s = 0.0, z = 0.0;
-#pragma unroll
-    for (int l = 0; l < NX; ++l) { s += Phi[i][l] * S[l]; z += Phi[i][l] * Z[l]; }
-    So[(size_t)i * Km1] = s;
-    Zo[(size_t)i * Km1] = z;
-  }
-}
-
-// xdot = f(x, u(t)) over [0, dt*sigma]  (first_order_hold.py:157-162), integrated in tau = t/sigma.
-template <class M>
-__device__ __forceinline__ void flow_interval(double* x, const double* u0, const double* u1, double sigma, double dt,
-                                              int n_sub) {
-  constexpr int NX = M::NX, NU = M::NU;
-  double du[NU];
-#pragma unroll
-  for (int j = 0; j < NU; ++j) du[j] = u1[j] - u0[j];
-  const int ns = (n_sub > 0) ? n_sub : auto_substeps(sigma, dt, u0, u1, NU);
-  const double h = dt / (double)ns, inv_dt = 1.0 / dt;
-  for (int s = 0; s < ns; ++s) {
-    const double t = (double)s * h;
-    double k1[NX], k2[NX], k3[NX], k4[NX], xs[NX], u[NU];
-#pragma unroll
-    for (int j = 0; j < NU; ++j) u[j] = u0[j] + (t * inv_dt) * du[j];
-    M::f_only(x, u, k1);
-#pragma unroll
-    for (int j = 0; j < NU; ++j) u[j] = u0[j] + ((t + 0.5 * h) * inv_dt) * du[j];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xs[i] = x[i] + 0.5 * h * sigma * k1[i];
-    M::f_only(xs, u, k2);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xs[i] = x[i] + 0.5 * h * sigma * k2[i];
-    M::f_only(xs, u, k3);
-#pragma unroll
-    for (int j = 0; j < NU; ++j) u[j] = u0[j] + ((t + h) * inv_dt) * du[j];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) xs[i] = x[i] + h * sigma * k3[i];
-    M::f_only(xs, u, k4);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] += (h * sigma / 6.0) * (k1[i] + 2.0 * k2[i] + 2.0 * k3[i] + k4[i]);
-  }
+  foh_rk4_body<M>(n_agents, K, n_sub, X, U, sigma_arr, A_bar, B_bar, C_bar, S_bar, z_bar);
 }
 
 template <class M>
 __global__ void __launch_bounds__(128)
-integrate_piecewise_kernel(int n_agents, int K, int n_sub, const double* __restrict__ X_lin,
-                           const double* __restrict__ U, const double* __restrict__ sigma_arr,
-                           double* __restrict__ X_nl) {
-  constexpr int NX = M::NX, NU = M::NU;
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (long long)n_agents * K) return;
-  const int agent = (int)(gid / K);
-  const int k = (int)(gid - (long long)agent * K);     // output column k
-  const double* Xa = X_lin + (size_t)agent * NX * K;
-  const double* Ua = U + (size_t)agent * NU * K;
-  double* Xo = X_nl + (size_t)agent * NX * K;
-  if (k == 0) {
-#pragma unroll
-    for (int i = 0; i < NX; ++i) Xo[(size_t)i * K] = Xa[(size_t)i * K];
-    return;
-  }
-  double x[NX], u0[NU], u1[NU];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) x[i] = Xa[(size_t)i * K + k - 1];
-#pragma unroll
-  for (int j = 0; j < NU; ++j) { u0[j] = Ua[(size_t)j * K + k - 1]; u1[j] = Ua[(size_t)j * K + k]; }
-  flow_interval<M>(x, u0, u1, sigma_arr[agent], 1.0 / (double)(K - 1), n_sub);
-#pragma unroll
-  for (int i = 0; i < NX; ++i) Xo[(size_t)i * K + k] = x[i];
+integrate_piecewise_kernel(int n_agents, int K, int n_sub, const double* __restrict__ X_lin, const double* __restrict__ U,
+                           const double* __restrict__ sigma_arr, double* __restrict__ X_nl) {
+  integrate_piecewise_body<M>(n_agents, K, n_sub, X_lin, U, sigma_arr, X_nl);
 }
 
 template <class M>
 __global__ void __launch_bounds__(128)
 integrate_full_kernel(int n_agents, int K, int n_sub, const double* __restrict__ x0, const double* __restrict__ U,
                       const double* __restrict__ sigma_arr, double* __restrict__ X_nl) {
-  constexpr int NX = M::NX, NU = M::NU;
-  const int agent = blockIdx.x * blockDim.x + threadIdx.x;
-  if (agent >= n_agents) return;
-  const double* Ua = U + (size_t)agent * NU * K;
-  double* Xo = X_nl + (size_t)agent * NX * K;
-  double x[NX];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) { x[i] = x0[(size_t)agent * NX + i]; Xo[(size_t)i * K] = x[i]; }
-  const double sigma = sigma_arr[agent], dt = 1.0 / (double)(K - 1);
-  for (int k = 0; k < K - 1; ++k) {
-    double u0[NU], u1[NU];
-#pragma unroll
-    for (int j = 0; j < NU; ++j) { u0[j] = Ua[(size_t)j * K + k]; u1[j] = Ua[(size_t)j * K + k + 1]; }
-    flow_interval<M>(x, u0, u1, sigma, dt, n_sub);
-#pragma unroll
-    for (int i = 0; i < NX; ++i) Xo[(size_t)i * K + k + 1] = x[i];
-  }
+  integrate_full_body<M>(n_agents, K, n_sub, x0, U, sigma_arr, X_nl);
 }
 
 }  // namespace scvx
@@ -339,8 +65,10 @@ extern "C" int scvx_foh_batched(int model_id, int n_agents, int K, int n_sub, co
       foh_rk4_kernel<SingleIntegrator><<<blocks, threads, 0, st>>>(n_agents, K, n_sub, X, U, sigma, A_bar, B_bar,
                                                                    C_bar, S_bar, z_bar);
       break;
-    default:
-      return bad_arg("model_id");
+    default: {
+      void* args[] = {&n_agents, &K, &n_sub, &X, &U, &sigma, &A_bar, &B_bar, &C_bar, &S_bar, &z_bar};
+      return user_model_launch(model_id, 0, blocks, threads, args, st, "scvx_foh_batched (user model)");
+    }
   }
   SCVX_CHECK_LAUNCH("scvx_foh_batched");
   return SCVX_OK;
@@ -362,8 +90,10 @@ extern "C" int scvx_integrate_piecewise_batched(int model_id, int n_agents, int 
     case SCVX_MODEL_SINGLE_INTEGRATOR:
       integrate_piecewise_kernel<SingleIntegrator><<<blocks, threads, 0, st>>>(n_agents, K, n_sub, X_lin, U, sigma, X_nl);
       break;
-    default:
-      return bad_arg("model_id");
+    default: {
+      void* args[] = {&n_agents, &K, &n_sub, &X_lin, &U, &sigma, &X_nl};
+      return user_model_launch(model_id, 1, blocks, threads, args, st, "scvx_integrate_piecewise_batched (user model)");
+    }
   }
   SCVX_CHECK_LAUNCH("scvx_integrate_piecewise_batched");
   return SCVX_OK;
@@ -384,8 +114,10 @@ extern "C" int scvx_integrate_full_batched(int model_id, int n_agents, int K, in
     case SCVX_MODEL_SINGLE_INTEGRATOR:
       integrate_full_kernel<SingleIntegrator><<<blocks, threads, 0, st>>>(n_agents, K, n_sub, x0, U, sigma, X_nl);
       break;
-    default:
-      return bad_arg("model_id");
+    default: {
+      void* args[] = {&n_agents, &K, &n_sub, &x0, &U, &sigma, &X_nl};
+      return user_model_launch(model_id, 2, blocks, threads, args, st, "scvx_integrate_full_batched (user model)");
+    }
   }
   SCVX_CHECK_LAUNCH("scvx_integrate_full_batched");
   return SCVX_OK;

@@ -1921,7 +1921,7 @@ extern "C" int scvx_order_by_iters(int n_agents, const int* iters, int* order, v
 extern "C" unsigned long long scvx_solve_workspace_bytes(int model_id, int n_agents, int K, int M, int n_nbr) {
   if (n_agents < 0 || K < 3 || M < 0 || n_nbr < 0) return 0ull;
   size_t tot;
-  switch (model_id) {
+  switch (solver_shape_of(model_id)) {
     case SCVX_MODEL_UNICYCLE: tot = solver_ws_total_doubles<Unicycle>(n_agents, K, M + n_nbr); break;
     case SCVX_MODEL_SINGLE_INTEGRATOR: tot = solver_ws_total_doubles<SingleIntegrator>(n_agents, K, M + n_nbr); break;
     default: return 0ull;
@@ -1950,7 +1950,7 @@ extern "C" int scvx_solve_batched(const scvx_solve_args* a, void* stream) {
     return SCVX_E_WORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  switch (a->model_id) {
+  switch (solver_shape_of(a->model_id)) {     // a registered user model runs through the kernel of its shape
     case SCVX_MODEL_UNICYCLE:
       if (!a->w_max) return bad_arg("w_max");
       return launch_ipm<Unicycle>(*a, st);

@@ -298,7 +298,7 @@ extern "C" int scvx_warm_start_batched(int model_id, int n_agents, int K, int M_
   if (M_max > 1024) return bad_arg("M_max > 1024");
   cudaStream_t st = (cudaStream_t)stream;
   const int P_max = 2 * M_max + 2;
-  switch (model_id) {
+  switch (solver_shape_of(model_id)) {
     case SCVX_MODEL_UNICYCLE: {
       const size_t smem = (size_t)P_max * 2 * sizeof(double) + (size_t)(2 * P_max + 2) * sizeof(int);
       warm_start_kernel<2><<<n_agents, 128, smem, st>>>(K, M_max, p0, p1, obs_c, obs_r, obs_count, clearance, X0, U0, status);

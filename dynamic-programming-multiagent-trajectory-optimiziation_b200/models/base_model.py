@@ -1,10 +1,11 @@
 """Model plug-in contract -- mirrors SCvx/models/base_model.py:7-88.
 
 Differences forced by the GPU path (no cvxpy objects exist here):
-  * a model that wants to run on the device names its compiled dynamics with the class attribute
-    `device_model_id` (one of scvx_b200._lib.MODEL_*); the device functions f/A/B live in
-    csrc/common.cuh.  `get_equations()` still returns host callables with the reference's shapes
-    so user code that probes f, A, B keeps working.
+  * the shipped models name their compiled dynamics with the class attribute `device_model_id` (one of
+    scvx_b200._lib.MODEL_*; device functions in csrc/common.cuh).  ANY OTHER model runs on the device by returning its
+    symbolic right-hand side from `symbolic_dynamics()`: f, A = df/dx, B = df/du are generated as CUDA C++ and compiled
+    with NVRTC at first use (scvx_b200/codegen.py).  `get_equations()` still returns host callables with the
+    reference's shapes so user code that probes f, A, B keeps working.
   * `get_constraints` returns a `ConstraintTables` descriptor (plain arrays) instead of a list of
     cvxpy constraints; the sub-problem kernel consumes exactly these tables.
 """
@@ -41,10 +42,27 @@ class ConstraintTables:
 class BaseModel(ABC):
     n_x = 0
     n_u = 0
-    device_model_id = None
+    position_dim = 2          # the first `position_dim` states are the position (obstacle / box / inter-agent rows act on them)
 
     def __init__(self):
         super().__init__()
+
+    def symbolic_dynamics(self):
+        """Optional hook of the GPU path: return (x_symbols, u_symbols, f_expr) as sympy objects -- the expression a model
+        written for the reference already holds when it builds its lambdas (unicycle_model.py:54-63) -- and the model's
+        dynamics are compiled for the device at first use (scvx_b200/codegen.py, NVRTC).  None: no device dynamics."""
+        return None
+
+    @property
+    def device_model_id(self):
+        """Id of the compiled device dynamics.  The shipped models override this with a constant; any other model gets one
+        by returning its symbolic right-hand side from `symbolic_dynamics()`."""
+        sym = self.symbolic_dynamics()
+        if sym is None:
+            return None
+        from .. import codegen
+        x_syms, u_syms, f_expr = sym
+        return codegen.register(x_syms, u_syms, f_expr, self.position_dim)
 
     @abstractmethod
     def get_equations(self):

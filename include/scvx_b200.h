@@ -36,6 +36,7 @@ extern "C" {
 /* model ids (SCvx/models/unicycle_model.py, SCvx/models/single_integrator_model.py) */
 #define SCVX_MODEL_UNICYCLE 0           /* n_x=3 n_u=2 d=2 */
 #define SCVX_MODEL_SINGLE_INTEGRATOR 1  /* n_x=3 n_u=3 d=3 */
+#define SCVX_MODEL_USER_BASE 16         /* ids >= this: models registered at run time, see scvx_user_model_register */
 
 /* error codes */
 #define SCVX_OK 0
@@ -54,6 +55,20 @@ int scvx_abi_version(void);
 const char* scvx_last_error(void);
 /* n_x, n_u, position dimension d of a model id; returns SCVX_E_BADARG for unknown ids */
 int scvx_model_dims(int model_id, int* n_x, int* n_u, int* d);
+
+/* ---------------------------------------------------------------------------------------------
+ * Model plug-in (BaseModel contract, SCvx/models/base_model.py:16-88; the reference accepts any model whose
+ * get_equations() returns f, A = df/dx, B = df/du -- its own models derive them with sympy, unicycle_model.py:54-63).
+ * `program` is a CUDA C++ translation unit holding `struct scvx::UserModel { NX, NU, D, eval, f_only }` generated from the
+ * user's symbolic dynamics, the stage-1 templates of csrc/foh_kernels.cuh and the three kernels scvx_user_foh /
+ * scvx_user_piecewise / scvx_user_full (scvx_b200/codegen.py builds it).  It is compiled for sm_100a with NVRTC
+ * (`nvrtc_path`: optional path of libnvrtc.so.12 to try first; the library dlopens it) and *model_id receives an id
+ * >= SCVX_MODEL_USER_BASE that the stage-1 entry points accept; stages 2-3 depend on a model's dimensions and constraint kind
+ * only and run a registered model through the kernels of its shape ((n_x, n_u, d) = (3, 2, 2) or (3, 3, 3); other shapes have
+ * stage 1 only and scvx_solve_batched returns SCVX_E_BADARG for them).  On a compile error: SCVX_E_BADARG and the compiler's
+ * log in scvx_user_model_log(). */
+int scvx_user_model_register(const char* program, int n_x, int n_u, int d, const char* nvrtc_path, int* model_id);
+const char* scvx_user_model_log(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Stage 1 -- first-order-hold discretisation.

@@ -15,10 +15,12 @@ scenes = bench.make_scenes(bench.N_AGENTS, 0)
 models = [UnicycleModel(r_init=o.x_init, r_final=o.x_final, obstacles=[(list(c), r) for c, r in o.obstacles]) for o in scenes]
 stream = torch.cuda.current_stream()
 for lanes in lanes_list:
-    for mode in ("eager", "graph", "graph4"):
+    for mode in ("eager", "lanegraph"):
         P = PipelinedSCvx(models, bench.K_NODES, n_lanes=lanes, max_iter=warm + steps + 4).start()
         P.run(warm)
-        if mode != "eager":
+        if mode == "lanegraph":
+            P.build_lane_graphs()
+        elif mode != "eager":
             P.build_graph(steps_per_graph=4 if mode == "graph4" else 1)
             # build_graph may have run one more eager step only if none had run: not the case here
         torch.cuda.synchronize()
@@ -26,6 +28,8 @@ for lanes in lanes_list:
         a.record(stream)
         if mode == "eager":
             P.run(steps)
+        elif mode == "lanegraph":
+            P.run_lane_graphs(steps, keep_history=False)
         else:
             P.run_graph(steps, keep_history=True)
         b.record(stream)
