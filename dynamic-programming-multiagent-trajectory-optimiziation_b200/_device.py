@@ -117,6 +117,67 @@ def consensus_update(P, Y, Lam, rho):
     return pr, du
 
 
+def consensus_update_x(X, d, Y, Lam, rho, out=None):
+    """consensus_update with the positions read in place from the agents' states X (n, n_x, K) (rows 0..d-1)."""
+    X, Y, Lam = _dev(X), _dev(Y), _dev(Lam)
+    n, n_x, K = X.shape
+    pr, du = out if out is not None else (torch.empty(n, dtype=F64, device=X.device), torch.empty(n, dtype=F64, device=X.device))
+    check(load().scvx_consensus_update_x(n, n_x, d, K, float(rho), ptr(X), ptr(Y), ptr(Lam), ptr(pr), ptr(du), stream_ptr()),
+          "scvx_consensus_update_x")
+    return pr, du
+
+
+class AdmmRoundTables:
+    """Outputs of scvx_admm_round_prep for (n_local agents, n_slots neighbour slots), allocated once."""
+
+    def __init__(self, model_id, n_local, n_slots, K, device):
+        _, _, d = MODEL_DIMS[model_id]
+        self.col_a = torch.empty((n_local, n_slots, d, K), dtype=F64, device=device)
+        self.col_b = torch.empty((n_local, n_slots, K), dtype=F64, device=device)
+        self.mask = torch.empty((n_local, n_slots), dtype=torch.uint8, device=device)
+        self.lin_p = torch.empty((n_local, d, K), dtype=F64, device=device)
+        self.quad_rho = torch.empty(n_local, dtype=F64, device=device)
+        self.aug_const = torch.empty(n_local, dtype=F64, device=device)
+
+
+def admm_round_prep(model_id, X_own, X_all, Y, Lam, d_min, rho, i0, tables, nbr_idx=None, mask_in=None):
+    """Collision half-spaces about (own reference, neighbours' trajectories), their right-hand sides d_min + a.Y_j and the
+    collapsed augmented-Lagrangian terms of the local agents, one launch (multi_agent_model.py:61-79, agent_solver.py:79-95)."""
+    X_own, X_all, Y, Lam = _dev(X_own), _dev(X_all), _dev(Y), _dev(Lam)
+    nl, _, K = X_own.shape
+    N = X_all.shape[0]
+    n_slots = tables.col_a.shape[1]
+    if nbr_idx is not None:
+        assert nbr_idx.is_cuda and nbr_idx.dtype == torch.int32 and nbr_idx.shape == (nl, n_slots) and nbr_idx.is_contiguous()
+    if mask_in is not None:
+        assert mask_in.is_cuda and mask_in.dtype == torch.uint8 and mask_in.shape == (nl, n_slots) and mask_in.is_contiguous()
+    check(load().scvx_admm_round_prep(model_id, nl, int(i0), N, K, n_slots, float(d_min), float(rho), ptr(X_own), ptr(X_all), ptr(Y),
+                                      ptr(Lam), ptr(nbr_idx), ptr(mask_in), ptr(tables.col_a), ptr(tables.col_b), ptr(tables.mask),
+                                      ptr(tables.lin_p), ptr(tables.quad_rho), ptr(tables.aug_const), stream_ptr()),
+          "scvx_admm_round_prep")
+    return tables
+
+
+def knn_select(d2, i0, k_sel, radius=None, out=None):
+    """k_sel nearest neighbours per row of the squared-distance table d2 (n_local, N) -- d2 is used as scratch."""
+    d2 = _dev(d2)
+    nl, N = d2.shape
+    if out is None:
+        out = torch.empty((nl, k_sel), dtype=torch.int32, device=d2.device)
+    check(load().scvx_knn_select(nl, int(i0), N, int(k_sel), float(radius) ** 2 if radius is not None else 0.0, ptr(d2), ptr(out),
+                                 stream_ptr()), "scvx_knn_select")
+    return out
+
+
+def radius_mask(d2, radius, out=None):
+    d2 = _dev(d2)
+    nl, N = d2.shape
+    if out is None:
+        out = torch.empty((nl, N), dtype=torch.uint8, device=d2.device)
+    check(load().scvx_radius_mask(nl, N, float(radius) ** 2, ptr(d2), ptr(out), stream_ptr()), "scvx_radius_mask")
+    return out
+
+
 def outer_update(model_id, M, conv_tol, X_new, U_new, nu_new, sigma_new, s_prime, X, U, sigma, tr_radius, active,
                  metrics):
     """One on-device outer-loop bookkeeping step (scvx_solver.py:82-111, :125-133); updates X, U, sigma,
@@ -130,13 +191,15 @@ def outer_update(model_id, M, conv_tol, X_new, U_new, nu_new, sigma_new, s_prime
 class SubproblemWorkspace:
     """Device scratch + output tensors for scvx_solve_batched, sized once for (n, K, M, n_nbr)."""
 
-    def __init__(self, model_id, n, K, M, n_nbr, device):
+    def __init__(self, model_id, n, K, M, n_nbr, device, X_out=None):
         n_x, n_u, d = MODEL_DIMS[model_id]
         self.model_id, self.n, self.K, self.M, self.n_nbr = model_id, n, K, M, n_nbr
         nbytes = int(load().scvx_solve_workspace_bytes(model_id, n, K, M, n_nbr))
         self.scratch = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=device)
         self.nbytes = nbytes
-        self.X = torch.empty((n, n_x, K), dtype=F64, device=device)
+        # X_out: the solver writes its states straight into a caller-owned buffer (BatchedADMM: the all-gather's send buffer)
+        self.X = torch.empty((n, n_x, K), dtype=F64, device=device) if X_out is None else X_out
+        assert self.X.shape == (n, n_x, K) and self.X.is_contiguous()
         self.U = torch.empty((n, n_u, K), dtype=F64, device=device)
         self.nu = torch.empty((n, n_x, K - 1), dtype=F64, device=device)
         self.sigma = torch.empty(n, dtype=F64, device=device)
@@ -291,12 +354,12 @@ def clearance_samples(model_id, X, U, sigma, obs_c, total_r, resolution=50):
     return out
 
 
-def cross_min_dist2(model_id, X_own, X_all):
+def cross_min_dist2(model_id, X_own, X_all, out=None):
     """min over k of the squared position distance between every local agent and every agent: (n_local, n_agents)."""
     X_own, X_all = _dev(X_own), _dev(X_all)
     nl, _, K = X_own.shape
     N = X_all.shape[0]
-    d2 = torch.empty((nl, N), dtype=F64, device=X_own.device)
+    d2 = torch.empty((nl, N), dtype=F64, device=X_own.device) if out is None else out
     check(load().scvx_cross_min_dist2(model_id, nl, N, K, ptr(X_own), ptr(X_all), ptr(d2), stream_ptr()), "scvx_cross_min_dist2")
     return d2
 

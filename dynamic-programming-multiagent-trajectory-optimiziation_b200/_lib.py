@@ -73,6 +73,10 @@ SIGNATURES = {
     "scvx_solve_workspace_bytes": (ctypes.c_ulonglong, [_c_int, _c_int, _c_int, _c_int, _c_int]),
     "scvx_solve_batched": (_c_int, [ctypes.POINTER(SolveArgs), _c_dp]),
     "scvx_consensus_update": (_c_int, [_c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),
+    "scvx_consensus_update_x": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 5 + [_c_dp]),
+    "scvx_admm_round_prep": (_c_int, [_c_int] * 6 + [_c_dbl, _c_dbl] + [_c_dp] * 12 + [_c_dp]),
+    "scvx_knn_select": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp]),
+    "scvx_radius_mask": (_c_int, [_c_int, _c_int, _c_dbl, _c_dp, _c_dp, _c_dp]),
     "scvx_outer_update": (_c_int, [_c_int, _c_int, _c_int, _c_int, _c_dbl] + [_c_dp] * 11 + [_c_dp]),
     "scvx_lti_qp_workspace_bytes": (ctypes.c_ulonglong, [_c_int, _c_int, _c_int, _c_int]),
     "scvx_lti_qp_batched": (_c_int, [ctypes.POINTER(LtiArgs), _c_dp]),

@@ -454,15 +454,33 @@ def allgather_shards(X_local, U_local, N, per, dist=None, group=None):
     return recv[:N, :n_x].contiguous(), recv[:N, n_x:].contiguous()
 
 
+def exchange_states(send, X_all, dist=None, group=None):
+    """The ONE collective of an ADMM round.  `send` (per, n_x, K): this rank's new states, zero-padded to `per` agents so that
+    every rank contributes the same count; `X_all` (world * per, n_x, K) receives all shards in rank (= agent) order, in place.
+    Only the last rank can be ragged, so rows 0..N-1 of X_all are exactly the N agents.  Any backend (NCCL on the GPUs, gloo in
+    the CPU tests); a single rank copies."""
+    if dist is None or dist.get_world_size(group) == 1:
+        X_all[:send.shape[0]].copy_(send)
+    else:
+        dist.all_gather_into_tensor(X_all, send, group=group)
+    return X_all
+
+
 class BatchedADMM:
     """Jacobi-sweep ADMM over N agents, optionally sharded across a process group.
 
-    Per round, for the local shard: FOH about the current own trajectory, obstacle + all-pairs inter-agent
-    linearisation about the gathered positions of the previous round, the QP/SOCP sub-problem
-    (agent_solver.py:79-102 collapsed to sum_j Y_j / sum_j Lambda_j), then ONE all-gather of
-    the new trajectories and the redundant per-j consensus update (admm_coordinator.py:80-96).
-    `si_variant=True` reproduces si_admm_coordinator.py:80-86 (trust region / obstacle linearisation about
-    the INITIAL references every round).
+    Per round, for the local shard: FOH about the current own trajectory, obstacle linearisation, ONE launch that builds the
+    inter-agent half-space tables, their right-hand sides and the collapsed augmented-Lagrangian terms in the solver's layout
+    (`scvx_admm_round_prep`: multi_agent_model.py:61-79 + agent_solver.py:79-95 collapsed to sum_j Y_j / sum_j Lambda_j,
+    SURVEY A.3), the QP/SOCP sub-problem, then ONE all-gather of the new states and the redundant per-j consensus update
+    (admm_coordinator.py:80-96).  `si_variant=True` reproduces si_admm_coordinator.py:80-86 (trust region / obstacle
+    linearisation about the INITIAL references every round).
+
+    The exchange is zero-copy: the solver writes its states straight into the all-gather's send buffer and every kernel reads
+    the gathered states in place (positions are the first d rows of a state block).  Inputs are only the neighbours' STATES:
+    the controls of other agents are never needed, so they are gathered once, after the last round.  No PyTorch arithmetic
+    runs between the exchange and the sub-problem solve; histories are accumulated into preallocated tables by device copies
+    and reduced once at the end.
     """
 
     def __init__(self, models, d_min, K, rho_admm=1.0, max_iter=10, si_variant=False, group=None, device=None,
@@ -485,22 +503,34 @@ class BatchedADMM:
         self.local = AgentBatch(models[self.i0:self.i1], K, device) if self.nl else None
         b = self.all
         dev = b.device
+        # exchange buffers: `send` holds this rank's (padded) shard of new states, `X_all` every rank's shard in agent order
+        self._send = torch.zeros((self.per, b.n_x, K), dtype=F64, device=dev)
+        self._X_all = torch.zeros((self.world * self.per, b.n_x, K), dtype=F64, device=dev)
         if self.nl:
             lb = self.local
             n_slots = self.neighbor_k if self.neighbor_k is not None else self.N
-            self.ws = _device.SubproblemWorkspace(lb.model_id, self.nl, K, lb.M, n_slots, dev)
+            self.ws = _device.SubproblemWorkspace(lb.model_id, self.nl, K, lb.M, n_slots, dev, X_out=self._send[:self.nl])
             self.mats = tuple(torch.empty((self.nl, r, K - 1), dtype=F64, device=dev)
                               for r in (b.n_x * b.n_x, b.n_x * b.n_u, b.n_x * b.n_u, b.n_x, b.n_x))
             self.obs_a = torch.empty((self.nl, lb.M, b.d, K), dtype=F64, device=dev)
             self.obs_b = torch.empty((self.nl, lb.M, K), dtype=F64, device=dev)
-            self.col_a = torch.empty((self.nl, n_slots, b.d, K), dtype=F64, device=dev)
-            self.col_b = torch.empty((self.nl, n_slots, K), dtype=F64, device=dev)
+            self.tab = _device.AdmmRoundTables(lb.model_id, self.nl, n_slots, K, dev)
+            self.col_a, self.col_b = self.tab.col_a, self.tab.col_b
+            self._U_cur = torch.empty((self.nl, b.n_u, K), dtype=F64, device=dev)
+            need_d2 = self.neighbor_k is not None or self.neighbor_radius is not None
+            self._d2 = torch.empty((self.nl, self.N), dtype=F64, device=dev) if need_d2 else None
+            self._nbr_idx = torch.empty((self.nl, n_slots), dtype=torch.int32, device=dev) if self.neighbor_k is not None else None
+            self._mask_in = torch.empty((self.nl, self.N), dtype=torch.uint8, device=dev) \
+                if (self.neighbor_k is None and self.neighbor_radius is not None) else None
+            self._order_buf = torch.empty(self.nl, dtype=torch.int32, device=dev)
         self.launches = 0
         self.profile = False             # True: CUDA events around the round's all-gather (see allgather_ms)
         self._gather_events = []
 
-    def _gather(self, X_local, U_local):
-        return allgather_shards(X_local, U_local, self.N, self.per, self.dist, self.group)
+    def _exchange(self):
+        """The ONE collective of a round: every rank's send buffer (its new states, padded to `per` agents so that all ranks
+        send the same count) lands in X_all in agent order.  One rank: a device-to-device copy."""
+        exchange_states(self._send, self._X_all, self.dist, self.group)
 
     def allgather_ms(self):
         """Device time of the all-gathers of the solves since the last call (profile=True), this rank; synchronises."""
@@ -512,97 +542,83 @@ class BatchedADMM:
 
     @property
     def allgather_bytes(self):
-        """Bytes every rank RECEIVES per round: the padded (X, U) shards of all ranks."""
+        """Bytes every rank RECEIVES per round: the padded state shards of all ranks."""
         b = self.all
-        return 0 if self.world == 1 else int(self.world * self.per * (b.n_x + b.n_u) * self.K * 8)
+        return 0 if self.world == 1 else int(self.world * self.per * b.n_x * self.K * 8)
 
     def solve(self, X_refs, U_refs, sigma_ref):
         """X_refs (N, n_x, K), U_refs (N, n_u, K) device tensors (every rank holds all of them).
         Returns dict(X, U (all agents, on every rank), primal_hist, dual_hist, objective (rounds, N_local))."""
         b = self.all
-        dev, K, N, d = b.device, self.K, self.N, b.d
-        X_all = _device._dev(X_refs).clone()
-        U_all = _device._dev(U_refs).clone()
-        Y = X_all[:, :d, :].contiguous().clone()                  # per-j consensus state (SURVEY 3.2)
+        dev, K, N, d, R = b.device, self.K, self.N, b.d, self.max_iter
+        X_refs, U_refs = _device._dev(X_refs), _device._dev(U_refs)
+        X_all = self._X_all[:N]                                   # gathered states, agent order (contiguous prefix)
+        X_all.copy_(X_refs)
+        Y = X_refs[:, :d, :].clone()                              # per-j consensus state (SURVEY 3.2); a private copy: it is
+        #                                                           updated in place and must not alias the caller's references
         Lam = torch.zeros_like(Y)
-        X0_loc = X_all[self.i0:self.i1].clone(); U0_loc = U_all[self.i0:self.i1].clone()
-        sig = torch.full((max(self.nl, 1),), float(sigma_ref), dtype=F64, device=dev)[:self.nl]
-        tr = torch.full((max(self.nl, 1),), float(TRUST_RADIUS0), dtype=F64, device=dev)[:self.nl]
-        primal_hist, dual_hist, objs = [], [], []
-        mask = None
+        pr_hist = torch.zeros((R, N), dtype=F64, device=dev); du_hist = torch.zeros((R, N), dtype=F64, device=dev)
+        obj_hist = torch.zeros((R, max(self.nl, 1)), dtype=F64, device=dev); const_hist = torch.zeros_like(obj_hist)
+        if self.nl:
+            lb = self.local
+            X0_loc = X_refs[self.i0:self.i1].clone(); U0_loc = U_refs[self.i0:self.i1].clone()
+            self._U_cur.copy_(U0_loc)
+            sig = torch.full((self.nl,), float(sigma_ref), dtype=F64, device=dev)
+            tr = torch.full((self.nl,), float(TRUST_RADIUS0), dtype=F64, device=dev)
         order = None
-        for _ in range(self.max_iter):
+        for r in range(R):
             if self.nl:
-                lb = self.local
-                X_loc = X_all[self.i0:self.i1].contiguous(); U_loc = U_all[self.i0:self.i1].contiguous()
-                Xr, Ur = (X0_loc, U0_loc) if self.si_variant else (X_loc, U_loc)
-                _device.foh(lb.model_id, X_loc, U_loc, sig, self.n_sub, out=self.mats)
+                X_loc = X_all[self.i0:self.i1]                    # own states of the previous round, read in place
+                Xr, Ur = (X0_loc, U0_loc) if self.si_variant else (X_loc, self._U_cur)
+                _device.foh(lb.model_id, X_loc, self._U_cur, sig, self.n_sub, out=self.mats)
                 if lb.M:
                     _device.linearize_obstacles(lb.model_id, Xr, lb.obs_c, lb.obs_clear, out=(self.obs_a, self.obs_b))
-                if self.neighbor_k is None:
-                    # a_ij about (own reference, neighbour's current trajectory); b = d_min + a.Y_j
-                    _device.linearize_collision(lb.model_id, Xr, X_all, self.d_min, i0=self.i0, out=(self.col_a, self.col_b))
-                    col_b = self.d_min + (self.col_a * Y[None]).sum(dim=2)
-                    mask = torch.ones((self.nl, N), dtype=torch.uint8, device=dev)
-                    mask[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = 0
-                    if self.neighbor_radius is not None:
-                        # neighbour culling (documented deviation for large N): keep j only if the trajectories come
-                        # within neighbor_radius at some node
-                        dist2 = ((Xr[:, None, :d, :] - X_all[None, :, :d, :]) ** 2).sum(dim=2).min(dim=2).values
-                        mask &= (dist2 <= self.neighbor_radius ** 2).to(torch.uint8)
-                    nact = mask.sum(dim=1).to(F64)
-                    # sum over ACTIVE neighbours of Y_j and Lambda_j  (all-pairs: total minus own)
-                    mY = torch.einsum("ij,jdk->idk", mask.to(F64), Y)
-                    mL = torch.einsum("ij,jdk->idk", mask.to(F64), Lam)
-                    yy = torch.einsum("ij,jdk->i", mask.to(F64), Y * Y)
-                    ly = torch.einsum("ij,jdk->i", mask.to(F64), Lam * Y)
-                else:
-                    # k nearest neighbours (minimum distance over the horizon), compact slot tables
-                    d2 = _device.cross_min_dist2(lb.model_id, Xr, X_all)
-                    d2[torch.arange(self.nl, device=dev), torch.arange(self.i0, self.i1, device=dev)] = float("inf")
-                    val, idx = torch.topk(d2, self.neighbor_k, dim=1, largest=False)
-                    sel = torch.isfinite(val)
-                    if self.neighbor_radius is not None:
-                        sel &= val <= self.neighbor_radius ** 2
-                    nbr_idx = torch.where(sel, idx, torch.full_like(idx, -1)).to(torch.int32)
-                    _device.linearize_collision_indexed(lb.model_id, Xr, X_all, nbr_idx, self.d_min, out=(self.col_a, self.col_b))
-                    selw = sel.to(F64)[:, :, None, None]
-                    Ysel = Y[idx] * selw; Lsel = Lam[idx] * selw                       # (nl, k, d, K)
-                    col_b = self.d_min + (self.col_a * Ysel).sum(dim=2)
-                    mask = sel.to(torch.uint8).contiguous()
-                    nact = sel.sum(dim=1).to(F64)
-                    mY = Ysel.sum(dim=1); mL = Lsel.sum(dim=1)
-                    yy = (Ysel * Ysel).sum(dim=(1, 2, 3)); ly = (Lsel * Ysel).sum(dim=(1, 2, 3))
-                    self.last_nbr_idx = nbr_idx
-                quad = self.rho * nact
-                lin = mL - self.rho * mY
+                nbr_idx = mask_in = None
+                if self._d2 is not None:
+                    # neighbour culling (documented deviations for large N): the k nearest neighbours by minimum distance over
+                    # the horizon (compact slot tables) and / or only neighbours that come within neighbor_radius at some node
+                    _device.cross_min_dist2(lb.model_id, Xr, X_all, out=self._d2)
+                    if self.neighbor_k is not None:
+                        nbr_idx = _device.knn_select(self._d2, self.i0, self.neighbor_k, self.neighbor_radius, out=self._nbr_idx)
+                        self.last_nbr_idx = nbr_idx
+                    else:
+                        mask_in = _device.radius_mask(self._d2, self.neighbor_radius, out=self._mask_in)
+                    self.launches += 2
+                # a_ij about (own reference, neighbour's current trajectory); b = d_min + a.Y_j; sum_j Lambda_j - rho sum_j Y_j
+                _device.admm_round_prep(lb.model_id, Xr, X_all, Y, Lam, self.d_min, self.rho, self.i0, self.tab,
+                                        nbr_idx=nbr_idx, mask_in=mask_in)
                 _device.solve_subproblem(self.ws, self.mats, Xr, Ur, sig, tr, lb.x_init, lb.x_final, lb.pos_lo,
                                          lb.pos_hi, lb.v_max, lb.w_max, self.obs_a, self.obs_b, WEIGHT_NU,
-                                         WEIGHT_SLACK, WEIGHT_SIGMA, col_a=self.col_a, col_b=col_b, col_mask=mask,
-                                         quad_rho=quad, lin_p=lin, weight_col=WEIGHT_COLLISION_SLACK,
-                                         max_iter=self.ipm_max_iter, block_order=order)
-                order = _device.order_by_iters(self.ws.iters)          # longest-first launch order for the next round
-                # constant terms of the augmented Lagrangian so that `objective` matches agent_solver.py:92-95
-                const = 0.5 * self.rho * yy - ly
-                objs.append((self.ws.objective + const).clone())
-                self.launches += 4 if lb.M else 3
-                X_new, U_new = self.ws.X, self.ws.U
-            else:
-                X_new = torch.empty((0, b.n_x, K), dtype=F64, device=dev); U_new = torch.empty((0, b.n_u, K), dtype=F64, device=dev)
+                                         WEIGHT_SLACK, WEIGHT_SIGMA, col_a=self.tab.col_a, col_b=self.tab.col_b,
+                                         col_mask=self.tab.mask, quad_rho=self.tab.quad_rho, lin_p=self.tab.lin_p,
+                                         weight_col=WEIGHT_COLLISION_SLACK, max_iter=self.ipm_max_iter, block_order=order)
+                order = _device.order_by_iters(self.ws.iters, out=self._order_buf)   # longest-first launch order for the next round
+                # the objective of agent_solver.py:92-95 = kernel objective + the constant of the collapsed Lagrangian
+                obj_hist[r, :self.nl].copy_(self.ws.objective); const_hist[r, :self.nl].copy_(self.tab.aug_const)
+                self._U_cur.copy_(self.ws.U)
+                self.launches += 5 if lb.M else 4
             if self.profile:
                 ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 ev[0].record()
-            X_all, U_all = self._gather(X_new, U_new)
+            self._exchange()
             if self.profile:
                 ev[1].record(); self._gather_events.append(ev)
-            X_all, U_all = X_all.clone(), U_all.clone()
-            P = X_all[:, :d, :].contiguous()
-            pr, du = _device.consensus_update(P, Y, Lam, self.rho)
+            _device.consensus_update_x(X_all, d, Y, Lam, self.rho, out=(pr_hist[r], du_hist[r]))
             self.launches += 1
-            primal_hist.append(pr.mean()); dual_hist.append(du.mean())
-        return {"X": X_all, "U": U_all, "Y": Y, "Lambda": Lam,
-                "primal_hist": torch.stack(primal_hist).cpu().tolist(), "dual_hist": torch.stack(dual_hist).cpu().tolist(),
-                "objective": torch.stack(objs) if objs else None, "mask": mask}
+        # other agents' controls are never an input of a round: one exchange at the end, for the caller
+        if self.dist is None or self.world == 1:
+            U_all = self._U_cur.clone() if self.nl else torch.empty((0, b.n_u, K), dtype=F64, device=dev)
+        else:
+            usend = torch.zeros((self.per, b.n_u, K), dtype=F64, device=dev)
+            if self.nl:
+                usend[:self.nl] = self._U_cur
+            urecv = torch.empty((self.world * self.per, b.n_u, K), dtype=F64, device=dev)
+            self.dist.all_gather_into_tensor(urecv, usend, group=self.group)
+            U_all = urecv[:N]
+        return {"X": X_all.clone(), "U": U_all, "Y": Y, "Lambda": Lam,
+                "primal_hist": pr_hist.mean(dim=1).cpu().tolist(), "dual_hist": du_hist.mean(dim=1).cpu().tolist(),
+                "objective": (obj_hist + const_hist)[:, :self.nl] if self.nl else None,
+                "mask": self.tab.mask if self.nl else None}
 
 
 SLAB_PENALTIES = (1e7, 1e8)      # exact-penalty weights of the hard slab rows, escalated while a slack remains

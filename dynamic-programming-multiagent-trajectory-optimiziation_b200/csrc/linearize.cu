@@ -109,14 +109,14 @@ __device__ __forceinline__ double block_max128(double v, double* sh) {
 
 // Y+ = (Y+P)/2; Lambda += rho (P - Y+); residual norms per agent      (admm_coordinator.py:80-96)
 __global__ void __launch_bounds__(128)
-consensus_kernel(int dK, double rho, const double* __restrict__ P, double* __restrict__ Y,
+consensus_kernel(int dK, size_t p_stride, double rho, const double* __restrict__ P, double* __restrict__ Y,
                  double* __restrict__ Lambda, double* __restrict__ pr, double* __restrict__ du) {
   __shared__ double sh[4];
   const int j = blockIdx.x;
   const size_t base = (size_t)j * dK;
   double spr = 0.0, sdu = 0.0;
   for (int e = threadIdx.x; e < dK; e += blockDim.x) {
-    const double p = P[base + e], yo = Y[base + e];
+    const double p = P[(size_t)j * p_stride + e], yo = Y[base + e];
     const double yn = 0.5 * (yo + p);
     Y[base + e] = yn;
     Lambda[base + e] += rho * (p - yn);
@@ -395,8 +395,19 @@ extern "C" int scvx_consensus_update(int n_agents, int d, int K, double rho, con
   if (n_agents < 0 || d < 1 || K < 1) return bad_arg("n_agents/d/K");
   if (n_agents == 0) return SCVX_OK;
   if (!P || !Y || !Lambda || !pr || !du) return bad_arg("null pointer");
-  consensus_kernel<<<n_agents, 128, 0, (cudaStream_t)stream>>>(d * K, rho, P, Y, Lambda, pr, du);
+  consensus_kernel<<<n_agents, 128, 0, (cudaStream_t)stream>>>(d * K, (size_t)d * K, rho, P, Y, Lambda, pr, du);
   SCVX_CHECK_LAUNCH("scvx_consensus_update");
+  return SCVX_OK;
+}
+
+extern "C" int scvx_consensus_update_x(int n_agents, int n_x, int d, int K, double rho, const double* X, double* Y, double* Lambda,
+                                       double* pr, double* du, void* stream) {
+  if (n_agents < 0 || d < 1 || K < 1 || n_x < d) return bad_arg("n_agents/n_x/d/K");
+  if (n_agents == 0) return SCVX_OK;
+  if (!X || !Y || !Lambda || !pr || !du) return bad_arg("null pointer");
+  // positions = the first d rows of every agent's (n_x, K) state block: read in place, no packed copy
+  consensus_kernel<<<n_agents, 128, 0, (cudaStream_t)stream>>>(d * K, (size_t)n_x * K, rho, X, Y, Lambda, pr, du);
+  SCVX_CHECK_LAUNCH("scvx_consensus_update_x");
   return SCVX_OK;
 }
 

@@ -27,6 +27,7 @@
 // run longest-first -- scvx_solve_args.block_order.)
 // Best-response (Nash game) terms: diagonal / linear / consecutive-difference quadratics and sigma == sigma_ref, see
 // scvx_solve_args.quad_diag .. fix_sigma in include/scvx_b200.h.
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 #include "reduce.cuh"
@@ -65,7 +66,10 @@ struct Dims {
   static constexpr int ST2 = 3;                           // corrector staging (e'tau of the interval, sigma-mu coefficient; the rest rides in dW)
   static constexpr int PER_STAGE = 3 * NSP + NJ + 3 * SD + SR + ST2;
   static constexpr int PER_STAGE_NOJAC = 3 * NSP + 3 * SD + SR + ST2;
-  static constexpr int SMALL = 64 + 9 * 24;               // globals + reduction scratch
+  static constexpr int SMALL = 64 + 9 * 24;               // globals + reduction scratch (one hinge group: <= 8 warps)
+  static constexpr int HSW = (D * D + 2 * D) | 1;         // per-stage partial results of a helper hinge group (odd stride)
+  // hinge groups G > 1: reduction scratch for 4 G warps, and the helpers' partial results
+  static constexpr int small_of(int G) { return 64 + (G == 1 ? 9 : 4 * G + 1) * 24; }
 };
 
 __device__ __forceinline__ double sgn(int e, int i) { return ((e >> i) & 1) ? -1.0 : 1.0; }
@@ -573,8 +577,13 @@ __device__ __forceinline__ constexpr double gG(int r, int i) {
 
 // ---- the kernel -----------------------------------------------------------------------------------
 // JSM: the interval Jacobians live in shared memory (compile-time, so that their loads are LDS and not generic LD)
-template <class M, bool JSM>
-__global__ void __launch_bounds__(SOLVER_MAX_THREADS, 1)
+// G: hinge groups.  G = 1: one thread per stage does everything (the shape of the independent-agent batches).  G > 1 (K <= 128):
+//    the block has G x 128 threads; thread (g, k) walks the g-th share of stage k's hinge rows in every row pass and the G - 1
+//    helper threads of a stage hand their partial sums to the stage's owner through shared memory.  With hundreds of inter-agent
+//    rows per stage (config 4: 255) the passes are >= 88 % of the solve and bound by one warp per scheduler's dependent-issue
+//    latency; the helper groups are extra warps on the same work (they also take part in the cyclic-reduction work items).
+template <class M, bool JSM, int G>
+__global__ void __launch_bounds__(G == 1 ? SOLVER_MAX_THREADS : 128 * G, 1)
 ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_feas, size_t jac_ws_offset) {
   using Dm = Dims<M>;
   constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
@@ -600,7 +609,16 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   double* red = gl + 64;                // [9][24] reduction scratch
   double* ST = Ck;                      // per-interval staging of the assembly pass (16 of SD doubles)
   // interval Jacobians [K][NJ]: shared memory when it fits, else a slice of the global workspace
-  double* JAC = JSM ? (red + 9 * 24) : ((double*)a.workspace + jac_ws_offset + (size_t)agent * K * NJ);
+  constexpr int RED = (G == 1 ? 9 : 4 * G + 1) * 24;
+  double* JAC = JSM ? (red + RED) : ((double*)a.workspace + jac_ws_offset + (size_t)agent * K * NJ);
+  double* HS = red + RED + (JSM ? (size_t)K * NJ : 0);       // [G-1][K][HSW] helper groups' partial results (G > 1 only)
+  constexpr int HSW = Dm::HSW;
+  // hinge share of this thread: group grp of G walks hinges [h_lo, h_hi) of stage kt
+  const int grp = (G == 1) ? 0 : tid / 128;
+  const int kt = (G == 1) ? tid : tid - grp * 128;
+  const int h_per = (NH + G - 1) / G;
+  const int h_lo = (G == 1) ? 0 : min(NH, grp * h_per), h_hi = (G == 1) ? NH : min(NH, h_lo + h_per);
+  const bool helper = (G > 1) && grp > 0;
   // globals: gl[0..3] = sigma, t_nu, t_x, t_u ; gl[4..7] = dg_aff ; gl[8..11] = dg ; gl[12..14] sG ; gl[15..17] lG ;
   // gl[18..33] = Gg/S 4x4 ; gl[34..37] = bg ; gl[40] flag ; gl[41] alpha_p ; gl[42] alpha_d ; gl[43] sigmu ; gl[44] mu
   // gl[45] comp ; gl[46..49] Y'b scratch
@@ -659,7 +677,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   auto hinge_w = [&](int h) -> double { return (h < Mobs) ? sc.hw_obs : sc.hw_col; };
   auto load_hinge_ab = [&](int h, int k) -> HingeData<D> {
     HingeData<D> r;
-    r.on = (h < NH) && hinge_on(h);
+    r.on = (h < h_hi) && hinge_on(h);
     r.b = 0.0; r.xi = 1.0; r.l1 = 1.0; r.l2 = 1.0;
 #pragma unroll
     for (int c = 0; c < D; ++c) r.a[c] = 0.0;
@@ -834,18 +852,23 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
         const double s = fmax(0.5 * (sc.v_max * sc.v_max - n2), 1e-8);
         ws.s.sB[k] = s; ws.s.lP[(size_t)Dm::R_V * K + k] = mu0 / s;
       }
-      for (int h = 0; h < NH; ++h) {
-        if (!hinge_on(h)) continue;
-        double ap = 0.0;
+    }
+  }
+  // hinge pairs: dual-feasible central start in closed form; every group initialises its own share
+  if (kt > 0 && kt < K - 1) {
+    const int k = kt;
+    const double* w = W + k * NSP;
+    for (int h = h_lo; h < h_hi; ++h) {
+      if (!hinge_on(h)) continue;
+      double ap = 0.0;
 #pragma unroll
-        for (int c = 0; c < D; ++c) ap += hinge_a(h, c, k) * w[c];
-        const double viol = hinge_b(h, k) - ap, hw = hinge_w(h);
-        const double disc = sqrt(hw * viol * hw * viol + 4.0 * mu0 * mu0);
-        const double num = (viol >= 0.0) ? hw * viol + disc : 4.0 * mu0 * mu0 / fmax(disc - hw * viol, 1e-300);
-        const double xi = (num + 2.0 * mu0) / (2.0 * hw);
-        const size_t o = (size_t)h * K + k;
-        ws.s.xi[o] = xi; ws.s.l1[o] = mu0 / (xi - viol); ws.s.l2[o] = mu0 / xi;
-      }
+      for (int c = 0; c < D; ++c) ap += hinge_a(h, c, k) * w[c];
+      const double viol = hinge_b(h, k) - ap, hw = hinge_w(h);
+      const double disc = sqrt(hw * viol * hw * viol + 4.0 * mu0 * mu0);
+      const double num = (viol >= 0.0) ? hw * viol + disc : 4.0 * mu0 * mu0 / fmax(disc - hw * viol, 1e-300);
+      const double xi = (num + 2.0 * mu0) / (2.0 * hw);
+      const size_t o = (size_t)h * K + k;
+      ws.s.xi[o] = xi; ws.s.l1[o] = mu0 / (xi - viol); ws.s.l2[o] = mu0 / xi;
     }
   }
   __syncthreads();
@@ -878,6 +901,57 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
     // The step of the PREVIOUS iteration is applied to the hinge pairs here, on the fly (the plain rows were updated by pass S).
     const double al_p0 = gl[41], al_d0 = gl[42];
     auto LPA = [&](size_t o) -> double { return ws.s.lP[o]; };
+    // One hinge pair of the residual pass: complementarity / stationarity statistics and the pair's contribution to the stage's
+    // Newton block (Dacc[c][c2], c, c2 < D), predictor rhs (bt_) and stationarity accumulator (bl_).
+    auto hinge_R = [&](int h, const HingeData<D>& hd, const double* w, auto& Dacc, double* bt_, double* bl_) {
+      double av[D], ap = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; }
+      const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
+      const double viol = hd.b - ap;
+      const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S);
+      const double w1 = l1 * rcp_fast(s1), w2 = l2 * rcp_fast(s2), rw = rcp_fast(w1 + w2), weff = w1 * w2 * rw;
+      const double th = w1 * hw * rw;                 // both primal residuals are zero by construction: rhs_xi = -hw
+      part[0] += s1 * l1 + s2 * l2;
+      part[2] = fmax(part[2], fabs(hw - l1 - l2));
+      part[16] += hw * xi;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        bt_[c] -= av[c] * th; bl_[c] -= av[c] * l1;
+#pragma unroll
+        for (int c2 = 0; c2 < D; ++c2) Dacc[c][c2] += weff * av[c] * av[c2];
+      }
+    };
+    // hinge rows in chunks of HINGE_CHUNK: all loads of a chunk are issued before its first use (memory-level parallelism is
+    // what a latency-bound walk over hundreds of neighbour rows needs)
+    auto hinge_R_range = [&](int k, const double* w, auto& Dacc, double* bt_, double* bl_) {
+      for (int h0 = h_lo; h0 < h_hi; h0 += HINGE_CHUNK) {
+        HingeData<D> hb[HINGE_CHUNK];
+#pragma unroll
+        for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge_apply(h0 + c, k, al_p0, al_d0);
+#pragma unroll
+        for (int c = 0; c < HINGE_CHUNK; ++c)
+          if (hb[c].on) hinge_R(h0 + c, hb[c], w, Dacc, bt_, bl_);
+      }
+    };
+    if (helper && kt > 0 && kt < K - 1) {
+      // helper group: its share of stage kt's hinge rows, partial sums to the stage's owner through shared memory
+      double Dh[D][D], bth[D], blh[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        bth[c] = 0.0; blh[c] = 0.0;
+#pragma unroll
+        for (int c2 = 0; c2 < D; ++c2) Dh[c][c2] = 0.0;
+      }
+      hinge_R_range(kt, W + kt * NSP, Dh, bth, blh);
+      double* hs = HS + ((size_t)(grp - 1) * K + kt) * HSW;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        hs[D * D + c] = bth[c]; hs[D * D + D + c] = blh[c];
+#pragma unroll
+        for (int c2 = 0; c2 < D; ++c2) hs[c * D + c2] = Dh[c][c2];
+      }
+    }
     for (int k = tid; k < K; k += nthr) {
       const double* w = W + k * NSP;
       const bool fr = (k > 0 && k < K - 1);
@@ -1025,39 +1099,8 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
             for (int j = 0; j < NU; ++j) Dl[NX + i][NX + j] += wgt * w[NX + i] * w[NX + j];
           }
         }
-        // hinge rows
-        // hinge rows in chunks of HINGE_CHUNK: all loads of a chunk are issued before its first use (memory-level
-        // parallelism is what a latency-bound walk over hundreds of neighbour rows needs)
-        auto hinge_body0 = [&](int h, const HingeData<D>& hd) {
-          double av[D], ap = 0.0;
-#pragma unroll
-          for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; }
-          const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
-          const double viol = hd.b - ap;
-          const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S), r1 = 0.0, r2 = 0.0;
-          const double w1 = l1 * rcp_fast(s1), w2 = l2 * rcp_fast(s2), rw = rcp_fast(w1 + w2), weff = w1 * w2 * rw;
-          const double t1 = w1 * r1, t2 = w2 * r2;
-          const double rhs_xi = -hw + t1 + t2;
-          const double th = t1 - w1 * rhs_xi * rw;
-          part[0] += s1 * l1 + s2 * l2;
-          part[1] = fmax(part[1], fmax(fabs(r1), fabs(r2)));
-          part[2] = fmax(part[2], fabs(hw - l1 - l2));
-          part[16] += hw * xi;
-#pragma unroll
-          for (int c = 0; c < D; ++c) {
-            bt[c] -= av[c] * th; bl[c] -= av[c] * l1;
-#pragma unroll
-            for (int c2 = 0; c2 < D; ++c2) Dl[c][c2] += weff * av[c] * av[c2];
-          }
-        };
-        for (int h0 = 0; h0 < NH; h0 += HINGE_CHUNK) {
-          HingeData<D> hb[HINGE_CHUNK];
-#pragma unroll
-          for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge_apply(h0 + c, k, al_p0, al_d0);
-#pragma unroll
-          for (int c = 0; c < HINGE_CHUNK; ++c)
-            if (hb[c].on) hinge_body0(h0 + c, hb[c]);
-        }
+        // hinge rows: this thread's share (all of them when G == 1)
+        hinge_R_range(k, w, Dl, bt, bl);
       }
       // quadratic / linear position terms (enter both the rhs and the stationarity residual)
 #pragma unroll
@@ -1115,6 +1158,17 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       double acc_t[NS], acc_l[NS];
 #pragma unroll
       for (int i = 0; i < NS; ++i) { acc_t[i] = dW[k * NSP + i]; acc_l[i] = dWa[k * NSP + i]; }
+      if (G > 1) {
+        for (int g = 1; g < G; ++g) {
+          const double* hs = HS + ((size_t)(g - 1) * K + k) * HSW;
+#pragma unroll
+          for (int c = 0; c < D; ++c) {
+            acc_t[c] += hs[D * D + c]; acc_l[c] += hs[D * D + D + c];
+#pragma unroll
+            for (int c2 = 0; c2 < D; ++c2) dk[c * NS + c2] += hs[c * D + c2];
+          }
+        }
+      }
       // interval k (this stage is the "previous" node): Jp
       {
         const double* jac = JAC + (size_t)k * NJ;
@@ -1407,6 +1461,64 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       double bta[NS], btb[NS];              // own-stage rhs pieces of the corrector (P), kept in registers across the reduction
 #pragma unroll
       for (int i = 0; i < NS; ++i) { bta[i] = 0.0; btb[i] = 0.0; }
+      // one hinge pair: P -- affine-step statistics and the pair's two pieces of the corrector rhs (bta_ * sigma mu + btb_);
+      //                 S -- step-length ratios of the final direction, the pair's step goes to the d* buffers
+      auto hinge_PS = [&](int h, const HingeData<D>& hd, int k, const double* w, const double* da, const double* dz, double* bta_,
+                          double* btb_) {
+        double av[D], ap = 0.0, ada = 0.0, adz = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
+        const size_t o = (size_t)h * K + k;
+        const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
+        const double viol = hd.b - ap;
+        const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S);
+        const double rs1 = rcp_fast(s1), rs2 = rcp_fast(s2);
+        const double w1 = l1 * rs1, w2 = l2 * rs2, rw = rcp_fast(w1 + w2);
+        // affine step of this hinge pair (sigma mu = 0, no second-order term; both primal residuals are zero by construction)
+        const double dxia = (-hw - w1 * ada) * rw;
+        const double ds1a = ada + dxia, ds2a = dxia;
+        const double dl1a = -l1 - w1 * ds1a, dl2a = -l2 - w2 * ds2a;
+        const double c1 = ds1a * dl1a, c2 = ds2a * dl2a;
+        if (P) {
+          qp = fmax(qp, fmax(-ds1a * rs1, -ds2a * rs2)); upd_d(dl1a, l1); upd_d(dl2a, l2);
+          pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += c1 + c2;
+          // t1 = (sigma mu - c1) / s1, t2 = (sigma mu - c2) / s2; rhs_xi = -hw + t1 + t2; th = t1 - w1 rhs_xi / (w1 + w2)
+          const double t1b = -c1 * rs1, t2b = -c2 * rs2;
+          const double tha = rs1 - w1 * (rs1 + rs2) * rw, thb = t1b - w1 * (-hw + t1b + t2b) * rw;
+#pragma unroll
+          for (int c = 0; c < D; ++c) { bta_[c] -= av[c] * tha; btb_[c] -= av[c] * thb; }
+          return;
+        }
+        const double t1 = (sigmu - c1) * rs1, t2 = (sigmu - c2) * rs2;
+        const double rhs_xi = -hw + t1 + t2;
+        const double dxi = (rhs_xi - w1 * adz) * rw;
+        const double ds1 = adz + dxi, ds2 = dxi;
+        const double dl1 = -l1 + (sigmu - c1) * rs1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) * rs2 - w2 * ds2;
+        qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
+        st_na(ws.dxi + o, dxi); st_na(ws.dl1 + o, dl1); st_na(ws.dl2 + o, dl2);
+      };
+      auto hinge_PS_range = [&](int k, const double* w, const double* da, const double* dz, double* bta_, double* btb_) {
+        for (int h0 = h_lo; h0 < h_hi; h0 += HINGE_CHUNK) {
+          HingeData<D> hb[HINGE_CHUNK];
+#pragma unroll
+          for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k, ws.s);
+#pragma unroll
+          for (int c = 0; c < HINGE_CHUNK; ++c)
+            if (hb[c].on) hinge_PS(h0 + c, hb[c], k, w, da, dz, bta_, btb_);
+        }
+      };
+      if (helper && kt > 0 && kt < K - 1) {
+        // helper group: its share of stage kt's hinge rows (P: partial rhs pieces to the stage's owner through shared memory)
+        double ha[D], hb_[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) { ha[c] = 0.0; hb_[c] = 0.0; }
+        hinge_PS_range(kt, W + kt * NSP, dWa + kt * NSP, dW + kt * NSP, ha, hb_);
+        if (P) {
+          double* hs = HS + ((size_t)(grp - 1) * K + kt) * HSW;
+#pragma unroll
+          for (int c = 0; c < D; ++c) { hs[c] = ha[c]; hs[D + c] = hb_[c]; }
+        }
+      }
       for (int k = tid; k < K; k += nthr) {
         const double* w = W + k * NSP;
         const double* da = dWa + k * NSP;
@@ -1516,47 +1628,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
               for (int j = 0; j < NU; ++j) { bta[NX + j] += ta * w[NX + j]; btb[NX + j] += tb * w[NX + j]; }
             }
           }
-          auto hinge_body = [&](int h, const HingeData<D>& hd) {
-            double av[D], ap = 0.0, ada = 0.0, adz = 0.0;
-#pragma unroll
-            for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
-            const size_t o = (size_t)h * K + k;
-            const double xi = hd.xi, l1 = hd.l1, l2 = hd.l2, hw = hinge_w(h);
-            const double viol = hd.b - ap;
-            const double s1 = fmax(xi - viol, TINY_S), s2 = fmax(xi, TINY_S);
-            const double rs1 = rcp_fast(s1), rs2 = rcp_fast(s2);
-            const double w1 = l1 * rs1, w2 = l2 * rs2, rw = rcp_fast(w1 + w2);
-            // affine step of this hinge pair (sigma mu = 0, no second-order term; both primal residuals are zero by construction)
-            const double dxia = (-hw - w1 * ada) * rw;
-            const double ds1a = ada + dxia, ds2a = dxia;
-            const double dl1a = -l1 - w1 * ds1a, dl2a = -l2 - w2 * ds2a;
-            const double c1 = ds1a * dl1a, c2 = ds2a * dl2a;
-            if (P) {
-              qp = fmax(qp, fmax(-ds1a * rs1, -ds2a * rs2)); upd_d(dl1a, l1); upd_d(dl2a, l2);
-              pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += c1 + c2;
-              // t1 = (sigma mu - c1) / s1, t2 = (sigma mu - c2) / s2; rhs_xi = -hw + t1 + t2; th = t1 - w1 rhs_xi / (w1 + w2)
-              const double t1b = -c1 * rs1, t2b = -c2 * rs2;
-              const double tha = rs1 - w1 * (rs1 + rs2) * rw, thb = t1b - w1 * (-hw + t1b + t2b) * rw;
-#pragma unroll
-              for (int c = 0; c < D; ++c) { bta[c] -= av[c] * tha; btb[c] -= av[c] * thb; }
-              return;
-            }
-            const double t1 = (sigmu - c1) * rs1, t2 = (sigmu - c2) * rs2;
-            const double rhs_xi = -hw + t1 + t2;
-            const double dxi = (rhs_xi - w1 * adz) * rw;
-            const double ds1 = adz + dxi, ds2 = dxi;
-            const double dl1 = -l1 + (sigmu - c1) * rs1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) * rs2 - w2 * ds2;
-            qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
-            st_na(ws.dxi + o, dxi); st_na(ws.dl1 + o, dl1); st_na(ws.dl2 + o, dl2);
-          };
-          for (int h0 = 0; h0 < NH; h0 += HINGE_CHUNK) {
-            HingeData<D> hb[HINGE_CHUNK];
-#pragma unroll
-            for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k, ws.s);
-#pragma unroll
-            for (int c = 0; c < HINGE_CHUNK; ++c)
-              if (hb[c].on) hinge_body(h0 + c, hb[c]);
-          }
+          hinge_PS_range(k, w, da, dz, bta, btb);
         }
         if (P) {
           // gradient of the smooth cost terms: independent of sigma mu
@@ -1631,6 +1703,13 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
             for (int i = 0; i < NX; ++i) { ek[i] = fma(smu, s0[i], dW[k * NSP + i]); ekm[i] = fma(smu, s1[i], dW[(k - 1) * NSP + i]); }
             JpT<Dm>(JAC + (size_t)k * NJ, ek, t);
             JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ekm, t2);
+            if (G > 1) {
+              for (int g = 1; g < G; ++g) {
+                const double* hs = HS + ((size_t)(g - 1) * K + k) * HSW;
+#pragma unroll
+                for (int c = 0; c < D; ++c) { bta[c] += hs[c]; btb[c] += hs[D + c]; }
+              }
+            }
 #pragma unroll
             for (int i = 0; i < NS; ++i) btb[i] = -(fma(smu, bta[i], btb[i]) + t[i] + t2[i]);
           }
@@ -1761,20 +1840,6 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
         for (int i = 0; i < NX; ++i) { No[(size_t)i * (K - 1) + k] = nu[i]; s += fabs(nu[i]); }
         pr[0] = fmax(pr[0], s);
       }
-      for (int h = 0; h < NH; ++h) {
-        double ap = 0.0;
-        const bool on = hinge_on(h);
-        if (on) {
-#pragma unroll
-          for (int c = 0; c < D; ++c) ap += hinge_a(h, c, k) * w[c];
-        }
-        const double v = on ? fmax(0.0, hinge_b(h, k) - ap) : 0.0;
-        if (h < Mobs) { a.s_prime[((size_t)agent * Mobs + h) * K + k] = v; pr[1] += v; }
-        else {
-          if (a.col_slack) a.col_slack[((size_t)agent * a.n_nbr + (h - Mobs)) * K + k] = v;
-          pr[2] += v;
-        }
-      }
 #pragma unroll
       for (int c = 0; c < D; ++c) {
         const double ql = qlin ? qlin[(size_t)c * K + k] : 0.0;
@@ -1786,6 +1851,25 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           double g, cv, ob;
           game_terms(k, i, w, g, cv, ob);
           pr[3] += ob / sc.cs;
+        }
+      }
+    }
+    // hinge values at every node (fixed end nodes included), every group its share
+    if (kt < K) {
+      const int k = kt;
+      const double* w = W + k * NSP;
+      for (int h = h_lo; h < h_hi; ++h) {
+        double ap = 0.0;
+        const bool on = hinge_on(h);
+        if (on) {
+#pragma unroll
+          for (int c = 0; c < D; ++c) ap += hinge_a(h, c, k) * w[c];
+        }
+        const double v = on ? fmax(0.0, hinge_b(h, k) - ap) : 0.0;
+        if (h < Mobs) { a.s_prime[((size_t)agent * Mobs + h) * K + k] = v; pr[1] += v; }
+        else {
+          if (a.col_slack) a.col_slack[((size_t)agent * a.n_nbr + (h - Mobs)) * K + k] = v;
+          pr[2] += v;
         }
       }
     }
@@ -1807,9 +1891,9 @@ constexpr size_t SMEM_LIMIT = 227 * 1024;
 constexpr size_t SMEM_TWO_PER_SM = 113 * 1024;
 
 template <class M>
-size_t solver_smem_bytes(int K, bool jac_in_smem) {
+size_t solver_smem_bytes(int K, bool jac_in_smem, int G = 1) {
   using Dm = Dims<M>;
-  return ((size_t)K * (jac_in_smem ? Dm::PER_STAGE : Dm::PER_STAGE_NOJAC) + Dm::SMALL) * sizeof(double);
+  return ((size_t)K * (jac_in_smem ? Dm::PER_STAGE : Dm::PER_STAGE_NOJAC) + Dm::small_of(G) + (size_t)(G - 1) * K * Dm::HSW) * sizeof(double);
 }
 template <class M>
 bool solver_jac_in_smem(int K) {
@@ -1817,6 +1901,19 @@ bool solver_jac_in_smem(int K) {
   if (with <= SMEM_TWO_PER_SM) return true;          // fits twice per SM either way
   if (without <= SMEM_TWO_PER_SM) return false;      // dropping the Jacobians buys the second block
   return with <= SMEM_LIMIT;                         // one block per SM: keep them on chip if possible
+}
+// Hinge groups: only where the block is alone on its SM anyway (its shared memory is > half an SM's) and a stage has enough
+// hinge rows to share out; SCVX_HINGE_GROUPS (1, 2 or 4) overrides the choice for experiments.
+template <class M>
+int solver_hinge_groups(int K, int NH) {
+  if (K > 128) return 1;
+  int want = (NH >= 64 && solver_smem_bytes<M>(K, solver_jac_in_smem<M>(K)) > SMEM_TWO_PER_SM) ? 2 : 1;
+  if (const char* e = getenv("SCVX_HINGE_GROUPS")) {
+    const int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) want = v;
+  }
+  while (want > 1 && solver_smem_bytes<M>(K, solver_jac_in_smem<M>(K), want) > SMEM_LIMIT) want >>= 1;
+  return want;
 }
 template <class M>
 size_t solver_ws_doubles_per_agent(int K, int NH) {
@@ -1831,17 +1928,24 @@ size_t solver_ws_total_doubles(int n_agents, int K, int NH) {
   return tot;
 }
 
+template <class M, bool JSM, int G>
+int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off) {
+  cudaError_t e = cudaFuncSetAttribute(ipm_kernel<M, JSM, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  ipm_kernel<M, JSM, G><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
+  SCVX_CHECK_LAUNCH("scvx_solve_batched");
+  return SCVX_OK;
+}
+
 template <class M>
 int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
   const bool jac_smem = solver_jac_in_smem<M>(a.K);
-  const size_t smem = solver_smem_bytes<M>(a.K, jac_smem);
+  const int G = solver_hinge_groups<M>(a.K, a.M + a.n_nbr);
+  const size_t smem = solver_smem_bytes<M>(a.K, jac_smem, G);
   if (smem > SMEM_LIMIT) {
     snprintf(g_last_error, sizeof(g_last_error), "K=%d needs %zu B of shared memory per agent (> 227 KB)", a.K, smem);
     return SCVX_E_UNSUPPORTED;
   }
-  cudaError_t e = jac_smem ? cudaFuncSetAttribute(ipm_kernel<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(ipm_kernel<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   int threads = ((a.K + 31) / 32) * 32;
   if (threads < 64) threads = 64;
   if (threads > SOLVER_MAX_THREADS) threads = SOLVER_MAX_THREADS;
@@ -1849,11 +1953,11 @@ int launch_ipm(const scvx_solve_args& a, cudaStream_t st) {
     snprintf(g_last_error, sizeof(g_last_error), "K=%d exceeds the %d threads of an agent's block", a.K, threads);
     return SCVX_E_UNSUPPORTED;
   }
+  if (G > 1) threads = 128 * G;
   const size_t jac_off = solver_ws_doubles_per_agent<M>(a.K, a.M + a.n_nbr) * (size_t)a.n_agents;
-  if (jac_smem) ipm_kernel<M, true><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
-  else ipm_kernel<M, false><<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
-  SCVX_CHECK_LAUNCH("scvx_solve_batched");
-  return SCVX_OK;
+  if (G == 4) return jac_smem ? launch_ipm_g<M, true, 4>(a, st, smem, threads, jac_off) : launch_ipm_g<M, false, 4>(a, st, smem, threads, jac_off);
+  if (G == 2) return jac_smem ? launch_ipm_g<M, true, 2>(a, st, smem, threads, jac_off) : launch_ipm_g<M, false, 2>(a, st, smem, threads, jac_off);
+  return jac_smem ? launch_ipm_g<M, true, 1>(a, st, smem, threads, jac_off) : launch_ipm_g<M, false, 1>(a, st, smem, threads, jac_off);
 }
 
 }  // namespace scvx

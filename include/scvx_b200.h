@@ -221,6 +221,32 @@ int scvx_solve_batched(const scvx_solve_args* args, void* stream);
  */
 int scvx_consensus_update(int n_agents, int d, int K, double rho, const double* P,
                           double* Y, double* Lambda, double* pr, double* du, void* stream);
+/* the same with the positions read in place from the agents' states X [n_agents][n_x][K] (rows 0..d-1) */
+int scvx_consensus_update_x(int n_agents, int n_x, int d, int K, double rho, const double* X, double* Y, double* Lambda,
+                            double* pr, double* du, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Everything of an ADMM round between the position exchange and the sub-problem solve, for the local agents
+ * i0 .. i0+n_local-1 of a rank, in scvx_solve_args' layout (csrc/admm_round.cu):
+ *   col_a[i][q][c][k]  normals of MultiAgentModel.linearize_collision (SCvx/models/multi_agent_model.py:61-79, SI twin
+ *                      SI_multi_agent_model.py:49-74) about (X_own_i, X_all_j),
+ *   col_b[i][q][k]     = d_min + a . Y_j   (collision rows of AgentSolver, SCvx/optimization/agent_solver.py:79-90),
+ *   lin_p[i][c][k]     = sum_j Lambda_j - rho sum_j Y_j,   quad_rho[i] = rho * #active neighbours,
+ *   aug_const[i]       = rho/2 sum ||Y_j||^2 - sum <Lambda_j, Y_j>     (agent_solver.py:92-95 collapsed),
+ *   mask_out[i][q]     1 = slot active.
+ * Slot q is agent q (nbr_idx NULL: all pairs, n_slots == n_agents) or agent nbr_idx[i][q] (-1 = empty); the own slot and slots
+ * with mask_in[i][q] == 0 (mask_in may be NULL) are inactive.  X_own [n_local][n_x][K], X_all [n_agents][n_x][K],
+ * Y, Lambda [n_agents][d][K]. */
+int scvx_admm_round_prep(int model_id, int n_local, int i0, int n_agents, int K, int n_slots, double d_min, double rho,
+                         const double* X_own, const double* X_all, const double* Y, const double* Lambda, const int* nbr_idx,
+                         const unsigned char* mask_in, double* col_a, double* col_b, unsigned char* mask_out, double* lin_p,
+                         double* quad_rho, double* aug_const, void* stream);
+/* k_sel nearest neighbours per local agent from scvx_cross_min_dist2's table d2 [n_local][n_agents] (used as scratch: selected
+ * entries are struck out), ascending, own column excluded, entries beyond radius2 (> 0) excluded, unused slots -1.
+ * No reference counterpart (the reference couples all pairs). */
+int scvx_knn_select(int n_local, int i0, int n_agents, int k_sel, double radius2, double* d2, int* nbr_idx, void* stream);
+/* mask[i][j] = d2[i][j] <= radius2 (neighbour culling of the all-pairs tables; no reference counterpart) */
+int scvx_radius_mask(int n_local, int n_agents, double radius2, const double* d2, unsigned char* mask, void* stream);
 
 /* On-device SCvx bookkeeping for one outer iteration of a batch (SCVXSolver.solve,
  * SCvx/optimization/scvx_solver.py:82-111, :125-133): metrics, convergence flag, trust-region update and

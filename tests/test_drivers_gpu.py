@@ -275,3 +275,27 @@ def test_config1_end_to_end_against_exact_lp_on_the_same_path(cuda):
         assert r["foh_err"] < 1e-9 or r["sigma_ref"] < 1e-6, r
     # both loops start from the same LP
     assert rows[0]["obj_gpu"] == pytest.approx(rec_o[0]["obj"], rel=1e-6)
+
+
+def test_batched_admm_single_integrator_leaves_its_inputs_alone_and_matches_the_twin_round_by_round(cuda):
+    """The single-integrator coordinator (si_admm_coordinator.py:80-86) linearises about the INITIAL references every round, and
+    for that model the position block is the whole state: the consensus state must be a private copy, not a view of the
+    caller's references (a round-2 bug: Y aliased X_refs, the references drifted with the consensus update).  Three rounds
+    against the oracle's Jacobi coordinator: same residual histories."""
+    from scvx_b200.batch import BatchedADMM
+    from scvx_b200.models.single_integrator_model import SingleIntegratorModel
+    N, Kc, d_min, sigma = 4, 16, 0.5, 12.0
+    rng = np.random.default_rng(9)
+    pts = rng.normal(size=(N, 3)); pts = 4 * pts / np.linalg.norm(pts, axis=1, keepdims=True)
+    models = [SingleIntegratorModel(r_init=q, r_final=-q, obstacles=[([0.0, 0.0, 0.0], 1.0)]) for q in pts]
+    oms = [omodels.single_integrator(r_init=q, r_final=-q, obstacles=[([0.0, 0.0, 0.0], 1.0)]) for q in pts]
+    XU = [m.initialize_trajectory(np.zeros((3, Kc)), np.zeros((3, Kc))) for m in models]
+    X_refs = [x + 0.05 * rng.normal(size=x.shape) * (j > 0) for j, (x, _) in enumerate(XU)]
+    U_refs = [u for _, u in XU]
+    X0 = torch.as_tensor(np.stack(X_refs)).to(cuda); U0 = torch.as_tensor(np.stack(U_refs)).to(cuda)
+    X0_keep, U0_keep = X0.clone(), U0.clone()
+    out = BatchedADMM(models, d_min, Kc, max_iter=3, si_variant=True).solve(X0, U0, sigma)
+    assert torch.equal(X0, X0_keep) and torch.equal(U0, U0_keep)
+    _, _, _, pj, dj, _ = oscvx.admm_solve(oms, d_min, Kc, X_refs, U_refs, sigma, max_iter=3, sweep="jacobi", si_variant=True)
+    np.testing.assert_allclose(out["primal_hist"], pj, rtol=2e-5)
+    np.testing.assert_allclose(out["dual_hist"], dj, rtol=2e-5)

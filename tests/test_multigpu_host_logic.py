@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from scvx_b200.batch import allgather_shards, shard_bounds
+from scvx_b200.batch import allgather_shards, exchange_states, shard_bounds
 
 
 def test_shard_bounds_cover_all_agents():
@@ -39,6 +39,11 @@ def _worker(rank, world, port, N, K, q):
             Xl = X[i0:i1] + _round; Ul = U[i0:i1] - _round
             Xa, Ua = allgather_shards(Xl, Ul, N, per, dist, None)
             ok = torch.equal(Xa, X + _round) and torch.equal(Ua, U - _round) and Xa.shape == (N, 3, K)
+            # the zero-copy exchange of BatchedADMM: padded send buffer in, all shards in agent order, in place
+            send = torch.zeros((per, 3, K), dtype=X.dtype); send[:i1 - i0] = Xl
+            X_all = torch.full((world * per, 3, K), float("nan"), dtype=X.dtype)
+            out = exchange_states(send, X_all, dist, None)
+            ok = ok and out is X_all and torch.equal(X_all[:N], X + _round)
             q.put((rank, _round, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -63,6 +68,8 @@ def test_single_process_is_identity():
     X = torch.zeros((3, 3, 4)); U = torch.ones((3, 2, 4))
     Xa, Ua = allgather_shards(X, U, 3, 3, None, None)
     assert Xa is X and Ua is U
+    X_all = torch.empty((3, 3, 4))
+    assert exchange_states(X + 2.0, X_all) is X_all and torch.equal(X_all, X + 2.0)
 
 
 def test_lane_bounds_of_the_pipelined_driver():

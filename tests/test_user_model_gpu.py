@@ -125,6 +125,7 @@ def test_compile_error_is_reported(cuda):
     s = sp.symbols("s")
     with pytest.raises(ValueError):
         codegen.register([s], [], sp.Matrix([s]), 1)              # a model without inputs
-    # a right-hand side that prints to something the compiler rejects surfaces as ScvxError with the NVRTC log attached
-    with pytest.raises(_lib.ScvxError, match="NVRTC"):
-        codegen.register([s], [sp.Symbol("q")], sp.Matrix([sp.Function("not_a_device_function")(s)]), 1)
+    # a model struct the compiler rejects surfaces as ScvxError-style failure with the NVRTC log available
+    prog = codegen.program_source("namespace scvx { struct UserModel { static constexpr int NX = 1, NU = 1, D = 1; }; }")
+    rc = lib.scvx_user_model_register(prog.encode(), 1, 1, 1, b"", ctypes.byref(mid))
+    assert rc == -1 and b"NVRTC" in lib.scvx_last_error() and len(lib.scvx_user_model_log()) > 0
