@@ -114,6 +114,7 @@ __device__ __forceinline__ void rhs_stage(double t, double inv_dt, double sigma,
       for (int l = 0; l < NX; ++l) acc += A[i][l] * Phi[l][j];
       kP[i][j] = acc;
     }
+  if (w == 0.0) return;      // a stage whose quadrature weight is zero (stage 2 of the 6th-order scheme) only feeds (x, Phi)
   double Pi[NX][NX];
   inv_small<NX>(Phi, Pi);
   const double wa = w * alpha, wb = w * beta;
@@ -147,6 +148,19 @@ __device__ __forceinline__ int auto_substeps(double sigma, double dt, const doub
   const double lam = fabs(sigma) * dt * um;
   double n = ceil(fmax(100.0 * sqrt(lam), 130.0 * pow(lam, 1.25)));
   n = fmin(fmax(n, 8.0), 8192.0);
+  return (int)n;
+}
+
+// Sub-steps of the 6th-order scheme for the same accuracy target (measured against the reference right-hand side integrated at
+// rtol 1e-13 over lambda = 0.02 .. 4, 24 random (x, u0, u1) each: the smallest n with error <= 1e-10 of scale was
+// 2, 3, 4, 5, 8, 10, 16, 20 at lambda = 0.02, 0.05, 0.12, 0.25, 0.5, 1, 2, 4  ~ 10 sqrt(lambda); the law adds ~25 % in n,
+// i.e. a factor ~4 in error, on top).
+__device__ __forceinline__ int auto_substeps_rk6(double sigma, double dt, const double* u0, const double* u1, int nu) {
+  double um = 1.0;
+  for (int j = 0; j < nu; ++j) um = fmax(um, fmax(fabs(u0[j]), fabs(u1[j])));
+  const double lam = fabs(sigma) * dt * um;
+  double n = ceil(11.5 * sqrt(lam)) + 1.0;
+  n = fmin(fmax(n, 2.0), 4096.0);
   return (int)n;
 }
 
@@ -184,8 +198,66 @@ __device__ __forceinline__ void foh_rk4_body(int n_agents, int K, int n_sub, con
 #pragma unroll
     for (int j = 0; j < NU; ++j) { Bm[i][j] = 0.0; Bp[i][j] = 0.0; }
   }
-  const int ns = (n_sub > 0) ? n_sub : auto_substeps(sigma, dt, u0, u1, NU);
-  const double h = dt / (double)ns;
+  if (n_sub <= 0) {
+    // Sub-step count chosen on the device: Butcher's 6th-order, 7-stage explicit Runge-Kutta scheme (1964).  Same splitting of
+    // the augmented state as below (the quadratures ride on the stage evaluations of (x, Phi) with the scheme's weights), and
+    // 4-5x fewer right-hand-side evaluations than RK4 for the same 1e-10 (50 x 4 vs 7 x 7 at lambda = 0.25).  A caller that
+    // asks for n_sub steps explicitly gets classical RK4, the scheme the interface names.
+    constexpr double c6[7] = {0.0, 1.0 / 3.0, 2.0 / 3.0, 1.0 / 3.0, 0.5, 0.5, 1.0};
+    constexpr double a6[7][6] = {{0, 0, 0, 0, 0, 0},
+                                 {1.0 / 3.0, 0, 0, 0, 0, 0},
+                                 {0, 2.0 / 3.0, 0, 0, 0, 0},
+                                 {1.0 / 12.0, 1.0 / 3.0, -1.0 / 12.0, 0, 0, 0},
+                                 {-1.0 / 16.0, 9.0 / 8.0, -3.0 / 16.0, -3.0 / 8.0, 0, 0},
+                                 {0, 9.0 / 8.0, -3.0 / 8.0, -3.0 / 4.0, 0.5, 0},
+                                 {9.0 / 44.0, -9.0 / 11.0, 63.0 / 44.0, 18.0 / 11.0, -16.0 / 11.0, 0}};
+    constexpr double b6[7] = {11.0 / 120.0, 0.0, 27.0 / 40.0, 27.0 / 40.0, -4.0 / 15.0, -4.0 / 15.0, 11.0 / 120.0};
+    const int ns6 = auto_substeps_rk6(sigma, dt, u0, u1, NU);
+    const double h = dt / (double)ns6;
+    for (int s = 0; s < ns6; ++s) {
+      const double t = (double)s * h;
+      double kx[7][NX], kP[7][NX][NX];
+#pragma unroll
+      for (int st = 0; st < 7; ++st) {
+        double xs[NX], Ps[NX][NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double ax = 0.0;
+#pragma unroll
+          for (int j = 0; j < st; ++j)
+            if (a6[st][j] != 0.0) ax += a6[st][j] * kx[j][i];
+          xs[i] = x[i] + h * ax;
+#pragma unroll
+          for (int l = 0; l < NX; ++l) {
+            double ap = 0.0;
+#pragma unroll
+            for (int j = 0; j < st; ++j)
+              if (a6[st][j] != 0.0) ap += a6[st][j] * kP[j][i][l];
+            Ps[i][l] = Phi[i][l] + h * ap;
+          }
+        }
+        rhs_stage<M>(t + c6[st] * h, inv_dt, sigma, u0, du, xs, Ps, kx[st], kP[st], b6[st] * h, Bm, Bp, S, Z);
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double ax = 0.0;
+#pragma unroll
+        for (int st = 0; st < 7; ++st)
+          if (b6[st] != 0.0) ax += b6[st] * kx[st][i];
+        x[i] += h * ax;
+#pragma unroll
+        for (int l = 0; l < NX; ++l) {
+          double ap = 0.0;
+#pragma unroll
+          for (int st = 0; st < 7; ++st)
+            if (b6[st] != 0.0) ap += b6[st] * kP[st][i][l];
+          Phi[i][l] += h * ap;
+        }
+      }
+    }
+  }
+  const int ns = (n_sub > 0) ? n_sub : 0;
+  const double h = (n_sub > 0) ? dt / (double)ns : 0.0;
   const double h2 = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
 
   for (int s = 0; s < ns; ++s) {

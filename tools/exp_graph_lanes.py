@@ -16,7 +16,7 @@ models = [UnicycleModel(r_init=o.x_init, r_final=o.x_final, obstacles=[(list(c),
 stream = torch.cuda.current_stream()
 for lanes in lanes_list:
     for mode in ("eager", "lanegraph"):
-        P = PipelinedSCvx(models, bench.K_NODES, n_lanes=lanes, max_iter=warm + steps + 4).start()
+        P = PipelinedSCvx(models, bench.K_NODES, n_lanes=lanes, max_iter=warm + steps + 4, adaptive_mu0=bool(int(os.environ.get('SCVX_ADAPTIVE_MU0', '0')))).start()
         P.run(warm)
         if mode == "lanegraph":
             P.build_lane_graphs()
@@ -37,4 +37,4 @@ for lanes in lanes_list:
         ms = a.elapsed_time(b)
         sig = float(sum(st[2].sum().item() for st in P.state))
         print(json.dumps({"lanes": lanes, "mode": mode, "ms_per_step": ms / steps, "agent_it_per_s": bench.N_AGENTS * steps / (ms * 1e-3),
-                          "checksum_sigma": sig, "optimal": float((P.status() == 0).double().mean().item()), "launches": P.launches}), flush=True)
+                          "checksum_sigma": sig, "optimal": float((P.status() == 0).double().mean().item()), "launches": P.launches, "mean_ipm_iters": float(P.ipm_iters().double().mean().item())}), flush=True)
