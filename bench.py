@@ -464,17 +464,18 @@ def run_ours(args, rank, world, local_rank):
 
 
 def ipm_flops_per_iteration(K, nx, nu, d, M):
-    """Algorithmic fp64 flop count of ONE interior-point iteration for one agent (DESIGN.md derives it):
-    row passes (5 sweeps over the 2^nx + 2^nx + 2^nu + 2d + 4 plain rows and M hinge pairs of every stage), assembly of
-    the block-tridiagonal matrix, block Cholesky with explicit inverse factors, two substitution sweeps for 4 border
-    columns + 1 rhs, one more pair of sweeps for the corrector."""
+    """Algorithmic fp64 flop count of ONE interior-point iteration for one agent, as the kernel is organised since round 2
+    (DESIGN.md 4.3): THREE row passes over the 2^nx + 2^nx + 2^nu + 2d + 4 plain rows and M hinge pairs of every stage (round 1
+    walked the rows five times: 750 k at K=100, M=8 against 577 k now), assembly of the block-tridiagonal matrix, block
+    Cholesky with explicit inverse factors, two substitution sweeps for 4 border columns + 1 rhs, one more pair of sweeps for
+    the corrector."""
     ns = nx + nu
     rows = 2 * (1 << nx) + (1 << nu) + 2 * d + 4
-    row_pass = rows * (2 * ns + 12) + M * (4 * d + 40)           # one sweep over a stage's rows
+    row_pass = rows * (2 * ns + 14) + M * (4 * d + 44)           # one sweep over a stage's rows (average of the three passes)
     assembly = 2 * (2 * nx * nx * ns + 2 * nx * ns * ns) + 2 * nx * ns * ns + 6 * nx * ns
     factor = 2 * ns ** 3 + ns ** 3 // 3 + ns ** 3 // 3 + 2 * ns ** 3      # update, Cholesky, inverse, Lo
     sweeps = 2 * 5 * 4 * ns * ns + 2 * 4 * ns * ns                          # (4+1 rhs) fwd+bwd, corrector fwd+bwd
-    return float(K * (5 * row_pass + assembly + factor + sweeps))
+    return float(K * (3 * row_pass + assembly + factor + sweeps))
 
 
 def measure_fp64_peak(lib, _lib, torch, dev):

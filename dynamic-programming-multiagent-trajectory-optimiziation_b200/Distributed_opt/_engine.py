@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from .._lib import LtiArgs, check, load, ptr, stream_ptr
+from .._lib import ScvxError, LtiArgs, check, load, ptr, stream_ptr
 
 F64 = torch.float64
 
@@ -85,4 +85,10 @@ def solve_sbar_qps(s_pos, r_dual, rho, col_h, col_g, c_S=1e6):
     s_pos, r_dual, col_h, col_g = s_pos.contiguous(), r_dual.contiguous(), col_h.contiguous(), col_g.contiguous()
     check(lib.scvx_sbar_qp_batched(R, T, nq, float(rho), float(c_S), ptr(s_pos), ptr(r_dual), ptr(col_h), ptr(col_g), ptr(sbar),
                                    ptr(S), ptr(wsb), wsb.numel() * 8, stream_ptr()), "scvx_sbar_qp_batched")
+    # The kernel has no per-(robot, t) status word; a non-finite input (coincident robots give NaN normals in the collision tables)
+    # or a step it had to abandon shows up as a non-finite result, which must not flow into the dual update unnoticed.
+    if not bool(torch.isfinite(col_g).all().item()):
+        raise ScvxError("scvx_sbar_qp_batched: non-finite collision normals (coincident robots?)")
+    if not bool((torch.isfinite(sbar).all() & torch.isfinite(S).all()).item()):
+        raise ScvxError("scvx_sbar_qp_batched: non-finite consensus solution")
     return sbar, S

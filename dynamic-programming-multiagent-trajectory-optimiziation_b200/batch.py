@@ -102,7 +102,8 @@ class BatchedSCvx:
             solver_events[0].record(torch.cuda.current_stream())
         _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
                                  b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
-                                 self.weight_sigma, max_iter=self.ipm_max_iter, block_order=self._order, mu0=self._mu0)
+                                 self.weight_sigma, max_iter=self.ipm_max_iter, block_order=self._order, mu0=self._mu0,
+                                 active=active)
         if solver_events is not None:
             solver_events[1].record(torch.cuda.current_stream())
         self._order = _device.order_by_iters(self.ws.iters, out=self._order_buf)

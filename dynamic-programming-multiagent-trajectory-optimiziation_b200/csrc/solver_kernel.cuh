@@ -124,6 +124,13 @@ struct AgentPtrs { RowState s; double *dxi, *dl1, *dl2; };
 // loads again before the next block barrier; with plain stores every later load of the stage would be ordered behind them.
 __device__ __forceinline__ void st_na(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v)); }
 
+// Bulk prefetch of a contiguous global range into L2 (TMA unit, one instruction per range, no registers or shared memory held):
+// address and size must be multiples of 16 bytes.
+__device__ __forceinline__ void l2_prefetch(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+constexpr int HINGE_PREFETCH = 8;   // hinge pairs fetched ahead into L2 by one thread of each hinge group
+
 // ---- per-stage linear forms ----------------------------------------------------------------------
 // nu-like combination for interval k: Jn w_{k+1} + Jp w_k + Js g_sigma (- zbar if AFFINE)
 template <class Dm, bool AFFINE>
@@ -606,6 +613,10 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   const int htid = threadIdx.x;                                // index of this thread among its block's hinge workers
   const int tid = leader ? htid : htid + (1 << 20);            // owner-thread index: out of every loop's range on a helper block
   auto CSYNC = [&]() { if (C > 1) cg::this_cluster().sync(); };
+  if (a.active && !a.active[agent]) {        // the agent's outer loop has converged: nothing to solve (uniform over the cluster)
+    if (threadIdx.x == 0 && leader) a.iters[agent] = 0;
+    return;
+  }
   const int Mobs = a.M, NH = a.M + a.n_nbr;
   // start value of the barrier parameter: per agent when the caller provides one (scvx_mu0_from_iters), else the default
   const double mu0_agent = a.mu0 ? a.mu0[agent] : 0.0;
@@ -760,6 +771,24 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       r.xi = src.xi[o]; r.l1 = src.l1[o]; r.l2 = src.l2[o];
     }
     return r;
+  };
+  // The walk over a stage share's hinge rows is a linear sweep over [h][c][k] tables far larger than L2 (config 4: 1.4-2.6 MB
+  // per agent and pass, 366 MB for 256 agents), latency-bound on DRAM with eight warps per SM (long scoreboard 3.0 warps per
+  // issue): one thread of every hinge group asks the TMA unit to pull the rows HINGE_PREFETCH pairs ahead into L2 while the
+  // group works on the current chunk.  Only the inter-agent rows (h >= Mobs; the obstacle rows are few) and only when the
+  // ranges are 16-byte aligned (K even).
+  const bool can_prefetch = (K % 2 == 0) && col_a && (kt == 1);       // stage 1: the first free stage of the group
+  auto prefetch_hinges = [&](int h0, bool with_step) {
+    if (!can_prefetch) return;
+    const int ha = max(h0 + HINGE_PREFETCH, Mobs), hb = min(ha + HINGE_CHUNK, h_hi);
+    if (hb <= ha) return;
+    const unsigned n = (unsigned)(hb - ha), rowb = (unsigned)K * 8u;
+    l2_prefetch(col_a + (size_t)(ha - Mobs) * D * K, n * D * rowb);
+    l2_prefetch(col_b + (size_t)(ha - Mobs) * K, n * rowb);
+    l2_prefetch(ws.s.xi + (size_t)ha * K, n * rowb); l2_prefetch(ws.s.l1 + (size_t)ha * K, n * rowb); l2_prefetch(ws.s.l2 + (size_t)ha * K, n * rowb);
+    if (with_step) {
+      l2_prefetch(ws.dxi + (size_t)ha * K, n * rowb); l2_prefetch(ws.dl1 + (size_t)ha * K, n * rowb); l2_prefetch(ws.dl2 + (size_t)ha * K, n * rowb);
+    }
   };
   // residual pass: the pending step of the hinge pair is applied, in place
   auto load_hinge_apply = [&](int h, int k, double al_p, double al_d) -> HingeData<D> {
@@ -995,6 +1024,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
     // what a latency-bound walk over hundreds of neighbour rows needs)
     auto hinge_R_range = [&](int k, const double* w, auto& Dacc, double* bt_, double* bl_) {
       for (int h0 = h_lo; h0 < h_hi; h0 += HINGE_CHUNK) {
+        prefetch_hinges(h0, true);
         HingeData<D> hb[HINGE_CHUNK];
 #pragma unroll
         for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge_apply(h0 + c, k, al_p0, al_d0);
@@ -1583,6 +1613,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       };
       auto hinge_PS_range = [&](int k, const double* w, const double* da, const double* dz, double* bta_, double* btb_) {
         for (int h0 = h_lo; h0 < h_hi; h0 += HINGE_CHUNK) {
+          prefetch_hinges(h0, false);
           HingeData<D> hb[HINGE_CHUNK];
 #pragma unroll
           for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k, ws.s);

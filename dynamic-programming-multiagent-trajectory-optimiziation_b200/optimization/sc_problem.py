@@ -6,6 +6,8 @@ reference builds a cvxpy graph and calls ECOS, `solve` uploads the parameters, r
 linearisation kernel about X_ref and the batched interior-point kernel with a batch of one
 (scvx_solve_batched), and downloads X, U, nu, sigma and the obstacle slacks.
 """
+import warnings
+
 import numpy as np
 import torch
 
@@ -67,10 +69,12 @@ class SCProblem:
         """Returns True on solver error (the reference's convention, sc_problem.py:95-105).
         Solver keyword arguments of the reference (solver="ECOS", warm_start=..., verbose=...) are accepted
         and ignored; `max_iter=` caps the interior-point iterations."""
-        try:
-            self._solve_device(max_iter=int(kwargs.get("max_iter", 0)))
-        except _lib.ScvxError:
-            raise
+        self._solve_device(max_iter=int(kwargs.get("max_iter", 0)))
+        if self.status == _lib.ST_MAXITER:
+            # the reference's solver would report "optimal_inaccurate" here and cvxpy lets that pass as success too; say so
+            warnings.warn(f"SCProblem.solve: the interior-point method stopped at its iteration cap ({self.iters}); the returned "
+                          "iterate is primal feasible but not certified optimal (prob.status == 'optimal_inaccurate')", RuntimeWarning,
+                          stacklevel=2)
         return self.status != _lib.ST_OPTIMAL and self.status != _lib.ST_MAXITER
 
     def get_variable(self, name):

@@ -201,6 +201,9 @@ typedef struct scvx_solve_args {
    * scvx_mu0_from_iters picks a small start for agents whose PREVIOUS solve was short (on the numpy twin, 200 sub-problems of the
    * bench scenes: mu0 = 0.1 after a solve of <= 10 iterations cuts the mean iteration count 11.8 -> 10.8, maximum unchanged). */
   const double *mu0;
+  /* Outer-loop activity flags (n_agents ints, NULL = all active): the block of an agent whose flag is 0 -- its outer loop has
+   * converged (scvx_outer_update) -- returns at once, iters = 0, every other output keeps its previous value. */
+  const int *active;
 } scvx_solve_args;
 
 /* order[r] = index of the agent with the r-th LARGEST iters (ties by index): a longest-first launch order for the next solve */

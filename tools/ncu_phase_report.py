@@ -46,12 +46,13 @@ def phases(src):
 
 if __name__ == "__main__":
     data = load(sys.argv[1])
-    src = sys.argv[2] if len(sys.argv) > 2 else "dynamic-programming-multiagent-trajectory-optimiziation_b200/csrc/solver.cu"
+    src = sys.argv[2] if len(sys.argv) > 2 else "dynamic-programming-multiagent-trajectory-optimiziation_b200/csrc/solver_kernel.cuh"
+    kfile = src.split("/")[-1]
     ph = phases(src)
     tot_s = sum(d[2] for d in data); tot_i = sum(d[3] for d in data)
     agg = collections.defaultdict(lambda: [0.0, 0.0, 0, collections.Counter()])
     for f, line, s, i, st, _ in data:
-        key = ph(line) if f == "solver.cu" else f
+        key = ph(line) if f == kfile else f
         a = agg[key]; a[0] += s; a[1] += i; a[2] += 1
         for k, v in st.items(): a[3][k] += v
     print(f"total samples {tot_s:.0f}, warp instructions {tot_i:.3e}, SASS instructions {len(data)}")
@@ -64,5 +65,5 @@ if __name__ == "__main__":
     print("\ntop lines:")
     srcl = open(src).read().split("\n")
     for (f, line), s in sorted(byline.items(), key=lambda kv: -kv[1])[:14]:
-        txt = srcl[line - 1].strip()[:110] if f == "solver.cu" else ""
+        txt = srcl[line - 1].strip()[:110] if f == kfile else ""
         print(f"- {100*s/tot_s:.1f}% {f}:{line} `{txt}`")
