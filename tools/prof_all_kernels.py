@@ -12,7 +12,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 
 KERNEL_REGEX = ("foh_rk4|integrate_|linearize_|ipm_kernel|outer_update|order_by_iters|consensus_kernel|lti_qp|sbar_|"
-                "slab_normals|warm_start|min_pair|min_obstacle|intersample|clearance_samples|cross_min")
+                "slab_normals|warm_start|min_pair|min_obstacle|intersample|clearance_samples|cross_min|admm_prep|knn_select|radius_mask|mu0_from_iters")
 METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,"
            "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,"
            "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,"
@@ -116,12 +116,26 @@ adm = BatchedADMM(ms3, 0.5, K, max_iter=1)
 timed("ADMM round: linearize_collision + ipm_kernel (n_nbr = 16) + consensus_kernel", lambda: adm.solve(X0, U0, 20.0),
       note=f"{N3} agents, all pairs, K={K}: latency-bound (16 blocks)")
 
+# ---------------------------------------------------------------- config 4: 256 single-integrator agents, all pairs, one ADMM round
+XU4 = [m.initialize_trajectory(np.zeros((3, K)), np.zeros((3, K))) for m in si]
+X4 = torch.as_tensor(np.stack([x for x, _ in XU4])).to(dev); U4 = torch.as_tensor(np.stack([u for _, u in XU4])).to(dev)
+adm4 = BatchedADMM(si, 0.5, K, max_iter=1, si_variant=True)
+timed("ADMM round, config 4: admm_prep_kernel<3> + ipm_kernel<SingleIntegrator, G=2> (n_nbr = 256) + consensus_kernel", lambda: adm4.solve(X4, U4, 20.0),
+      alg_bytes=ns * 30 * 8 * 255 * K * 36, note=f"{ns} agents, all pairs, K={K}: 255 hinge pairs per stage, two hinge groups per block; "
+      "alg_bytes assumes 36 interior-point iterations")
+tab4 = _device.AdmmRoundTables(_lib.MODEL_SINGLE_INTEGRATOR, ns, ns, K, dev)
+Y4 = X4[:, :3].clone(); L4 = torch.zeros_like(Y4)
+timed("admm_prep_kernel<3>", lambda: _device.admm_round_prep(_lib.MODEL_SINGLE_INTEGRATOR, X4, X4, Y4, L4, 0.5, 1.0, 0, tab4),
+      alg_bytes=ns * ns * K * 8 * (3 + 3 + 3 + 4), note=f"{ns} x {ns} slots x K={K}: reads X, Y, Lambda of every neighbour, writes a (3) and b")
+
 # ---------------------------------------------------------------- neighbour tables at config-5 scale (2048 agents x K = 200)
 N5, K5 = 2048, 200
 X5 = torch.as_tensor(rng.normal(size=(N5, 3, K5)) * 5.0, device=dev)
 d2 = timed("cross_min_dist2_kernel", lambda: _device.cross_min_dist2(_lib.MODEL_UNICYCLE, X5, X5), alg_bytes=N5 * 2 * K5 * 8 * 2 + N5 * N5 * 8,
            alg_flops=N5 * N5 * K5 * 5.0, note=f"{N5} x {N5} pairs x K={K5}; the N^2 K re-reads are served from L2 / shared memory")
-idx = torch.topk(d2 + torch.eye(N5, device=dev, dtype=F64) * 1e30, 16, dim=1, largest=False).indices.to(torch.int32)
+idx = timed("knn_select_kernel", lambda: _device.knn_select(d2.clone(), 0, 16), alg_bytes=N5 * N5 * 8 + N5 * 16 * 4,
+            note=f"{N5} rows x {N5} candidates, 16 nearest (one warp per row, 16 rounds of warp arg-min over the row)")
+timed("radius_mask_kernel", lambda: _device.radius_mask(d2, 1.0), alg_bytes=N5 * N5 * 9, note=f"{N5} x {N5} table")
 timed("linearize_collision_indexed_kernel", lambda: _device.linearize_collision_indexed(_lib.MODEL_UNICYCLE, X5, X5, idx, 0.5),
       alg_bytes=N5 * 16 * K5 * 8 * (2 + 3), note=f"{N5} agents x 16 neighbours x K={K5}")
 timed("min_pair_distance_kernel", lambda: _device.min_inter_agent_distance(X5), alg_bytes=N5 * 3 * K5 * 8 + N5 * N5 * 8,
