@@ -1,7 +1,9 @@
 """Oracle restatement of the reference's convex sub-problem (stage 3) as an explicit LP / QP.
 
-TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED against cvxpy+ECOS (absent
-from the build container); exact solver = HiGHS; compare optimal VALUES, not minimisers.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).  PARITY UNPINNED against cvxpy+ECOS / CLARABEL: the
+packages are absent from the build container AND from the GPU box (tools/probe_solvers.py, log
+profiles/r02_probe_solvers_gpu_box.json), upstream pins no versions and holds no golden values for
+this stage; exact solver = HiGHS; compare optimal VALUES, not minimisers.
 
 Follows (reference paths):
   SCvx/optimization/sc_problem.py:21-26    variables X, U, nu, sigma>=0
