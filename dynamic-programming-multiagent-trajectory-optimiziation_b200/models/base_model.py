@@ -98,3 +98,48 @@ class BaseModel(ABC):
 
     def u_redim(self, U):
         return U
+
+
+def straight_line_guess(x_init, x_final, X, U):
+    """The reference models' `initialize_trajectory` (unicycle_model.py:73-83, single_integrator_model.py:65-77): states on
+    the straight line from x_init to x_final, zero inputs, written into the caller's arrays.  Column k is
+    (K-1-k)/(K-1) * x_init + k/(K-1) * x_final -- evaluated for all k at once with the same two products and one sum per
+    entry, hence bit-identical to the reference's loop."""
+    n = X.shape[1]
+    k = np.arange(n)
+    X[:, :] = np.outer(x_init, (n - 1 - k) / (n - 1)) + np.outer(x_final, k / (n - 1))
+    U[:] = 0
+    return X, U
+
+
+class AgentCollection:
+    """What MultiAgentModel / SI_MultiAgentModel share (multi_agent_model.py:8-79, SI_multi_agent_model.py:7-74): a list of
+    per-agent models built from parameter dicts, the minimum separation, and per-agent accessors."""
+    _MODEL = None
+    _KEYS = ()
+
+    def __init__(self, agent_params, d_min=1.0):
+        self.N, self.d_min = len(agent_params), d_min
+        self.models = [self._build(params) for params in agent_params]
+
+    def _build(self, params):
+        return self._MODEL(**{k: params[k] for k in self._KEYS if params.get(k) is not None})
+
+    def get_local_dynamics(self, i):
+        return self.models[i].get_equations()
+
+    def get_static_constraints(self, i, X=None, U=None, X_ref=None, U_ref=None):
+        return self.models[i].get_constraints(X, U, X_ref, U_ref)
+
+    def get_objective(self, i, X=None, U=None, X_ref=None, U_ref=None):
+        return self.models[i].get_objective(X, U, X_ref, U_ref)
+
+    def _pair(self, X_ref_i, X_ref_j):
+        """One (i, j) pair through the batched stage-2 kernel (n_local = n_agents = 1): (a (d, K), b (K,))."""
+        import torch
+        from .. import _device
+        dev = torch.device("cuda")
+        Xi = torch.as_tensor(np.ascontiguousarray(X_ref_i, dtype=np.float64)).unsqueeze(0).to(dev)
+        Xj = torch.as_tensor(np.ascontiguousarray(X_ref_j, dtype=np.float64)).unsqueeze(0).to(dev)
+        a, b = _device.linearize_collision(self._MODEL.device_model_id, Xi, Xj, self.d_min, i0=1)   # i0=1: slot 0 is not "self"
+        return a[0, 0].cpu().numpy(), b[0, 0].cpu().numpy()

@@ -5,7 +5,7 @@ import numpy as np
 
 from .. import _lib
 from ..global_parameters import K
-from .base_model import BaseModel, ConstraintTables, SlackValue
+from .base_model import BaseModel, ConstraintTables, SlackValue, straight_line_guess
 
 MARGIN_OBS = 0.0   # SCvx/config/SI_default_game.py:9
 
@@ -42,13 +42,8 @@ class SingleIntegratorModel(BaseModel):
         return self.f, self.A, self.B
 
     def initialize_trajectory(self, X: np.ndarray, U: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        K_local = X.shape[1]
-        for k in range(K_local):
-            alpha1 = (K_local - 1 - k) / (K_local - 1)
-            alpha2 = k / (K_local - 1)
-            X[:, k] = alpha1 * self.x_init + alpha2 * self.x_final
-        U[:] = 0
-        return X, U
+        """Straight line in state space, zero controls; fills and returns the caller's arrays."""
+        return straight_line_guess(self.x_init, self.x_final, X, U)
 
     def get_constraints(self, X=None, U=None, X_ref=None, U_ref=None) -> ConstraintTables:
         """single_integrator_model.py:79-128: boundary, ||u_k||_2 <= v_max, box, spherical obstacles."""

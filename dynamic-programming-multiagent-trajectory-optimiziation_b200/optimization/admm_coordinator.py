@@ -1,7 +1,7 @@
 """ADMMCoordinator -- mirrors SCvx/optimization/admm_coordinator.py:13-118.
 
-`solve` is the reference's sequential Gauss-Seidel sweep, statement for statement, with the per-agent
-discretisation and sub-problem on the GPU.  `solve_batched` is the device-resident Jacobi variant
+`solve` keeps the reference's sequential Gauss-Seidel order (agent i sees the trajectories agents 0..i-1 produced in the
+same round) with the per-agent discretisation and sub-problem on the GPU.  `solve_batched` is the device-resident Jacobi variant
 (`scvx_b200.batch.BatchedADMM`): all agents of a round in one launch, shardable over GPUs with one
 all-gather per round (SURVEY hard part 5 documents the Gauss-Seidel -> Jacobi difference).
 """
@@ -24,60 +24,60 @@ class ADMMCoordinator:
     _SI_VARIANT = False
 
     def __init__(self, multi_agent_model, rho_admm: float = 1.0, max_iter: int = 10, K=K):
-        self.model = multi_agent_model
-        self.N = multi_agent_model.N
-        self.rho_admm = rho_admm
-        self.max_iter = max_iter
-        self.K = K
-        self.agent_solvers = []
-        self.discretizers = []
-        for i in range(self.N):
-            self.agent_solvers.append(self._SOLVER(i, multi_agent_model, rho_admm, K))
-            self.discretizers.append(FirstOrderHold(multi_agent_model.models[i], K))
+        self.model, self.N, self.K = multi_agent_model, multi_agent_model.N, K
+        self.rho_admm, self.max_iter = rho_admm, max_iter
+        self.agent_solvers = [self._SOLVER(i, multi_agent_model, rho_admm, K) for i in range(self.N)]
+        self.discretizers = [FirstOrderHold(m, K) for m in multi_agent_model.models]
+
+    # -- the literal coordinator: agents one after the other (Gauss-Seidel), host arrays in and out ------------------------
+    def _reset_consensus(self, X_refs):
+        """Every agent's copy Y_j of neighbour j starts at j's reference positions, the multipliers at zero."""
+        d = self._D
+        for solver in self.agent_solvers:
+            for j, holder in solver.Y.items():
+                holder.value = np.array(X_refs[j][0:d, :])
+                solver.Lambda[j].value = np.zeros((d, self.K))
+
+    def _agent_round(self, i, X_now, U_now, X_refs, U_refs, sigma_ref):
+        """Agent i's sub-problem of this round about its current trajectory (the single-integrator coordinator keeps
+        linearising about the INITIAL references, si_admm_coordinator.py:80-86); returns (X_i, U_i, p_i)."""
+        mats = self.discretizers[i].calculate_discretization(X_now[i], U_now[i], sigma_ref)
+        about = (X_refs[i], U_refs[i]) if self._SI_VARIANT else (X_now[i], U_now[i])
+        solver = self.agent_solvers[i]
+        solver.setup(about[0], about[1], sigma_ref, mats, {j: X_now[j] for j in range(self.N) if j != i})
+        X_i, U_i, _nu, _slacks, p_i = solver.solve(solver="ECOS")
+        return X_i, U_i, p_i
+
+    def _consensus_round(self, positions):
+        """Y_j <- (Y_j + p_j) / 2, Lambda_j += rho (p_j - Y_j) in every agent's copy; mean residuals over all (i, j) copies."""
+        primal, dual = [], []
+        for solver in self.agent_solvers:
+            for j, holder in solver.Y.items():
+                before = holder.value
+                after = 0.5 * (before + positions[j])
+                holder.value = after
+                solver.Lambda[j].value = solver.Lambda[j].value + self.rho_admm * (positions[j] - after)
+                primal.append(primal_residual(positions[j], after))
+                dual.append(dual_residual(after, before))
+        return float(np.mean(primal)), float(np.mean(dual))
 
     def solve(self, X_refs: list, U_refs: list, sigma_ref: float, verbose: bool = True):
-        d, K = self._D, self.K
-        for solver in self.agent_solvers:
-            for j in solver.Y:
-                solver.Y[j].value = np.array(X_refs[j][0:d, :])
-                solver.Lambda[j].value = np.zeros((d, K))
-        X_curr = list(X_refs)
-        U_curr = list(U_refs)
-        primal_hist, dual_hist = [], []
-        t0 = time.time()
-        for it in range(self.max_iter):
-            new_positions = [None] * self.N
-            for i, solver in enumerate(self.agent_solvers):
-                mats = self.discretizers[i].calculate_discretization(X_curr[i], U_curr[i], sigma_ref)
-                neighbor_refs = {j: X_curr[j] for j in range(self.N) if j != i}
-                if self._SI_VARIANT:     # si_admm_coordinator.py:80-86: the INITIAL references every round
-                    solver.setup(X_refs[i], U_refs[i], sigma_ref, mats, neighbor_refs)
-                else:
-                    solver.setup(X_curr[i], U_curr[i], sigma_ref, mats, neighbor_refs)
-                X_i, U_i, nu_i, slacks_i, p_i = solver.solve(solver="ECOS")
-                X_curr[i], U_curr[i] = X_i, U_i
-                new_positions[i] = p_i
-            pr_vals, du_vals = [], []
-            for solver in self.agent_solvers:
-                for j in solver.Y:
-                    p_j = new_positions[j]
-                    Y_old = solver.Y[j].value
-                    Y_new = 0.5 * (Y_old + p_j)
-                    solver.Y[j].value = Y_new
-                    solver.Lambda[j].value = solver.Lambda[j].value + self.rho_admm * (p_j - Y_new)
-                    pr_vals.append(primal_residual(p_j, Y_new))
-                    du_vals.append(dual_residual(Y_new, Y_old))
-            pr_avg = float(np.mean(pr_vals))
-            du_avg = float(np.mean(du_vals))
-            primal_hist.append(pr_avg)
-            dual_hist.append(du_avg)
+        self._reset_consensus(X_refs)
+        X_now, U_now = list(X_refs), list(U_refs)
+        history = {"primal": [], "dual": []}
+        started = time.time()
+        for rnd in range(self.max_iter):
+            positions = {}
+            for i in range(self.N):
+                X_now[i], U_now[i], positions[i] = self._agent_round(i, X_now, U_now, X_refs, U_refs, sigma_ref)
+            pr, du = self._consensus_round(positions)
+            history["primal"].append(pr); history["dual"].append(du)
             if verbose:
-                print_iteration(it, nu_norm=0.0, slack_norm=0.0, primal_res=pr_avg, dual_res=du_avg, dx=0.0, ds=0.0,
-                                sigma=sigma_ref, tr_radius=self.rho_admm)
-        runtime = time.time() - t0
+                print_iteration(rnd, nu_norm=0.0, slack_norm=0.0, primal_res=pr, dual_res=du, dx=0.0, ds=0.0, sigma=sigma_ref,
+                                tr_radius=self.rho_admm)
         if verbose:
-            print_summary(len(primal_hist), sigma_ref, runtime)
-        return X_curr, U_curr, sigma_ref, primal_hist, dual_hist
+            print_summary(len(history["primal"]), sigma_ref, time.time() - started)
+        return X_now, U_now, sigma_ref, history["primal"], history["dual"]
 
     def solve_batched(self, X_refs: list, U_refs: list, sigma_ref: float, group=None, neighbor_radius=None):
         """Jacobi rounds on the device (and across the ranks of `group`).  Same return tuple as `solve`."""

@@ -57,6 +57,8 @@ class AgentBestResponse:
         self.Y_params: Dict[int, _Holder] = {j: _Holder((self._D, K)) for j in range(multi_agent_model.N) if j != i}
         self.X_prev_param = _Holder((3, K))
         self.scp = None
+    def _after_slabs(self, X_ref, U_ref, sigma_ref):
+        """Hook for model-specific refreshes that follow the slab update (the single-integrator game's inter-sample rows)."""
 
     def setup(self, X_ref, U_ref, sigma_ref: float, discr_mats: Tuple, neighbour_refs: Dict[int, np.ndarray], X_prev,
               neighbour_prev_refs: Dict[int, np.ndarray], tr_radius: float = TRUST_RADIUS0) -> None:
@@ -70,6 +72,7 @@ class AgentBestResponse:
                                      neighbour_prev_pos=neighbour_prev_pos)
         # normals along X_prev -> neighbour_prev so that the slabs hold at the previous iterate (agent_best_response.py:66-72)
         self.model.update_slabs(np.asarray(X_prev)[0:d, :], neighbour_prev_pos)
+        self._after_slabs(X_ref, U_ref, sigma_ref)
         A_bar, B_bar, C_bar, S_bar, z_bar = discr_mats
         self.scp.set_parameters(
             A_bar=np.array(A_bar), B_bar=np.array(B_bar), C_bar=np.array(C_bar), S_bar=np.array(S_bar), z_bar=np.array(z_bar),
