@@ -1,6 +1,4 @@
 """SingleIntegratorModel -- mirrors SCvx/models/single_integrator_model.py:12-141 (3-D, f = u)."""
-from typing import List, Optional, Tuple
-
 import numpy as np
 
 from .. import _lib
@@ -10,38 +8,29 @@ from .base_model import BaseModel, ConstraintTables, SlackValue, straight_line_g
 MARGIN_OBS = 0.0   # SCvx/config/SI_default_game.py:9
 
 
+_DEFAULT_SPHERES = (([-5.0, -4.0, -5.0], 2.0), ([0.0, 0.0, 4.0], 2.0))   # the reference's two default obstacles
+
+
 class SingleIntegratorModel(BaseModel):
-    n_x = 3
-    n_u = 3
+    n_x = n_u = 3
     device_model_id = _lib.MODEL_SINGLE_INTEGRATOR
 
-    def __init__(
-        self,
-        r_init: np.ndarray = np.array([-8.0, -8.0, -8.0]),
-        r_final: np.ndarray = np.array([8.0, 8.0, 8.0]),
-        v_max: float = 1.0,
-        bounds: Tuple[float, float] = (-10.0, 10.0),
-        robot_radius: float = 0.5,
-        obstacles: Optional[List[Tuple[List[float], float]]] = None,
-    ):
+    def __init__(self, r_init=(-8.0, -8.0, -8.0), r_final=(8.0, 8.0, 8.0), v_max=1.0, bounds=(-10.0, 10.0),
+                 robot_radius=0.5, obstacles=None):
+        """Same keywords and defaults as single_integrator_model.py:17-51; the dynamics x' = u need no symbolic build."""
         super().__init__()
-        self.x_init = np.asarray(r_init, dtype=float).reshape(-1)
-        self.x_final = np.asarray(r_final, dtype=float).reshape(-1)
-        self.v_max = v_max
+        self.x_init, self.x_final = (np.array(r, dtype=float).ravel() for r in (r_init, r_final))
+        self.v_max, self.robot_radius = v_max, robot_radius
         self.lower_bound, self.upper_bound = bounds
-        self.robot_radius = robot_radius
-        self.obstacles = (
-            obstacles if obstacles is not None else [([-5.0, -4.0, -5.0], 2.0), ([0.0, 0.0, 4.0], 2.0)]
-        )
+        self.obstacles = [(list(c), r) for c, r in _DEFAULT_SPHERES] if obstacles is None else obstacles
         self.s_prime = [SlackValue(K) for _ in self.obstacles]
-        self.f = lambda x, u: u
-        self.A = lambda x, u: np.zeros((self.n_x, self.n_x))
-        self.B = lambda x, u: np.eye(self.n_x)
+        eye, zero = np.eye(3), np.zeros((3, 3))
+        self.f, self.A, self.B = (lambda x, u: u), (lambda x, u: zero.copy()), (lambda x, u: eye.copy())
 
-    def get_equations(self) -> Tuple:
+    def get_equations(self):
         return self.f, self.A, self.B
 
-    def initialize_trajectory(self, X: np.ndarray, U: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    def initialize_trajectory(self, X, U):
         """Straight line in state space, zero controls; fills and returns the caller's arrays."""
         return straight_line_guess(self.x_init, self.x_final, X, U)
 

@@ -18,18 +18,17 @@ def _gap_norm(a, b) -> float:
     return float(np.sqrt(np.dot(gap, gap)))
 
 
-def primal_residual(p_j: np.ndarray, Y_ij: np.ndarray) -> float:
+def primal_residual(p_j, Y_ij):
     """||p_j - Y_ij||_F: how far agent j's own position trajectory is from the copy its neighbours hold."""
     return _gap_norm(p_j, Y_ij)
 
 
-def dual_residual(Y_new: np.ndarray, Y_old: np.ndarray) -> float:
+def dual_residual(Y_new, Y_old):
     """||Y_new - Y_old||_F: how far one consensus update moved the shared copy."""
     return _gap_norm(Y_new, Y_old)
 
 
-def update_rho_admm(rho: float, primal_res: float, dual_res: float,
-                    mu: float = 10.0, tau_inc: float = 2.0, tau_dec: float = 2.0) -> float:
+def update_rho_admm(rho, primal_res, dual_res, mu=10.0, tau_inc=2.0, tau_dec=2.0):
     """Residual balancing: rho grows by tau_inc when the primal residual dominates the dual one by more than the factor mu,
     shrinks by tau_dec in the opposite case, and is left alone in between."""
     grow = primal_res > mu * dual_res
