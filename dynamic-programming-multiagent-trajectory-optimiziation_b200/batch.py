@@ -64,6 +64,13 @@ class AgentBatch:
         return X.contiguous(), U
 
 
+# Barrier start of a warm sub-problem (the reference trajectory is the previous solution): every agent whose previous solve ended
+# within MU0_POLICY[0] interior-point iterations starts at mu = MU0_POLICY[1], the others (iteration cap hit) at the cold default.
+# Measured on the bench workload (tools/exp_mu0_policy.py, gpurun_out/r02p_mu0_policy.txt): (10, 0.1) 2.66 ms/step, (1000, 1e-2) 2.68,
+# (1000, 1e-3) 2.28, (1000, 1e-4) 2.56; no start 3.02.
+MU0_POLICY = (1000, 1e-3, 10.0)
+
+
 class BatchedSCvx:
     """All agents run the reference's outer loop in lock step on the device."""
 
@@ -71,9 +78,9 @@ class BatchedSCvx:
                  weight_nu=WEIGHT_NU, weight_slack=WEIGHT_SLACK, weight_sigma=WEIGHT_SIGMA, n_sub=0,
                  ipm_max_iter=0, device=None, batch=None, adaptive_mu0=False):
         self.batch = batch if batch is not None else AgentBatch(models, K, device)
-        # adaptive_mu0: agents whose previous sub-problem took <= 10 interior-point iterations start the next one at mu = 0.1
-        # instead of 10 (measured on the numpy twin only so far, hence off by default)
+        # adaptive_mu0: warm sub-problems start at a small barrier parameter (MU0_POLICY) instead of the cold default 10
         self.adaptive_mu0 = bool(adaptive_mu0)
+        self.mu0_policy = MU0_POLICY      # (easy_max_iters, mu0_easy, mu0_hard) of scvx_mu0_from_iters
         self._mu0 = None
         b = self.batch
         self.K, self.max_iter, self.tr_radius0, self.conv_tol = K, max_iter, tr_radius0, conv_tol
@@ -108,7 +115,7 @@ class BatchedSCvx:
             solver_events[1].record(torch.cuda.current_stream())
         self._order = _device.order_by_iters(self.ws.iters, out=self._order_buf)
         if self.adaptive_mu0:
-            self._mu0 = _device.mu0_from_iters(self.ws.iters, out=self._mu0_buf)
+            self._mu0 = _device.mu0_from_iters(self.ws.iters, self._mu0_buf, *self.mu0_policy)
             self.launches += 1
         _device.outer_update(b.model_id, b.M, self.conv_tol, self.ws.X, self.ws.U, self.ws.nu, self.ws.sigma,
                              self.ws.s_prime, X, U, sigma, tr, active, metrics_row)

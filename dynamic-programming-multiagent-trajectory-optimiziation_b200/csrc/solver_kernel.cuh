@@ -1535,6 +1535,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       constexpr bool P = (PASS == 1);
       CSYNC();                              // the direction this pass walks (dWa / dW) and sigma mu are final in the leader
       const double sigmu = gll[43];                                        // valid in PASS 3 (written by the tail of PASS 1)
+      const double om = P ? 1.0 : gll[56];                                 // weight of the second-order term (PASS 3; see the tail of PASS 1)
       double pr[13];
 #pragma unroll
       for (int i = 0; i < 13; ++i) pr[i] = 0.0;
@@ -1550,7 +1551,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       // per-row kernel.  P: returns the two pieces of tau (ta * sigma mu + tb).  S: stores the multiplier step to `pd`
       // (and the slack step of the nonlinear ball row to `psd`).
       auto row = [&](double l, double gz_h, double gdza, double gdz, double& ta, double& tb, double& dl_out, const double* ps = nullptr,
-                     double* ds_out = nullptr) {
+                     double* ds_out = nullptr, double* t0_out = nullptr) {
         const double s = ps ? *ps : fmax(-gz_h, TINY_S);          // stored slack only for the nonlinear ball row
         const double rs = rcp_fast(s);
         const double rp = ps ? gz_h + s : 0.0, wgt = l * rs;
@@ -1559,10 +1560,11 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
         if (P) {
           qp = fmax(qp, -dsa * rs); upd_d(dla, l);
           pr[2] += dsa * l; pr[3] += s * dla; pr[4] += c2;
-          ta = rs; tb = (l * rp - c2) * rs;
+          ta = rs; tb = -c2 * rs;                                  // tau = ta * sigma mu + om * tb (+ t0: only the ball row has r_p != 0)
+          if (t0_out) *t0_out = l * rp * rs;
           return;
         }
-        const double ds = -rp - gdz, dl = -l + (sigmu - c2) * rs - wgt * ds;
+        const double ds = -rp - gdz, dl = -l + (sigmu - om * c2) * rs - wgt * ds;
         qp = fmax(qp, -ds * rs); upd_d(dl, l);
         dl_out = dl;
         if (ds_out) *ds_out = ds;
@@ -1572,13 +1574,16 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
       for (int r = 0; r < (P ? 1 : NPLAIN); ++r) dlr[r] = 0.0;
       auto DLR = [&](int r) -> double& { return dlr[P ? 0 : r]; };
 
-      double bta[NS], btb[NS];              // own-stage rhs pieces of the corrector (P), kept in registers across the reduction
+      // own-stage rhs pieces of the corrector (P), kept in registers across the reduction: bta * sigma mu + om * btb + bt0, where
+      // om weighs the second-order term (known, like sigma mu, only after the reduction)
+      double bta[NS], btb[NS], bt0[P ? NS : 1];
 #pragma unroll
-      for (int i = 0; i < NS; ++i) { bta[i] = 0.0; btb[i] = 0.0; }
-      // one hinge pair: P -- affine-step statistics and the pair's two pieces of the corrector rhs (bta_ * sigma mu + btb_);
+      for (int i = 0; i < NS; ++i) { bta[i] = 0.0; btb[i] = 0.0; bt0[P ? i : 0] = 0.0; }
+      auto BT0 = [&](int i) -> double& { return bt0[P ? i : 0]; };
+      // one hinge pair: P -- affine-step statistics and the pair's three pieces of the corrector rhs (bta_ * sigma mu + om * btb_ + bt0_);
       //                 S -- step-length ratios of the final direction, the pair's step goes to the d* buffers
       auto hinge_PS = [&](int h, const HingeData<D>& hd, int k, const double* w, const double* da, const double* dz, double* bta_,
-                          double* btb_) {
+                          double* btb_, double* bt0_) {
         double av[D], ap = 0.0, ada = 0.0, adz = 0.0;
 #pragma unroll
         for (int c = 0; c < D; ++c) { av[c] = hd.a[c]; ap += av[c] * w[c]; ada += av[c] * da[c]; adz += av[c] * dz[c]; }
@@ -1598,20 +1603,20 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           pr[2] += ds1a * l1 + ds2a * l2; pr[3] += s1 * dl1a + s2 * dl2a; pr[4] += c1 + c2;
           // t1 = (sigma mu - c1) / s1, t2 = (sigma mu - c2) / s2; rhs_xi = -hw + t1 + t2; th = t1 - w1 rhs_xi / (w1 + w2)
           const double t1b = -c1 * rs1, t2b = -c2 * rs2;
-          const double tha = rs1 - w1 * (rs1 + rs2) * rw, thb = t1b - w1 * (-hw + t1b + t2b) * rw;
+          const double tha = rs1 - w1 * (rs1 + rs2) * rw, thb = t1b - w1 * (t1b + t2b) * rw, th0 = w1 * hw * rw;
 #pragma unroll
-          for (int c = 0; c < D; ++c) { bta_[c] -= av[c] * tha; btb_[c] -= av[c] * thb; }
+          for (int c = 0; c < D; ++c) { bta_[c] -= av[c] * tha; btb_[c] -= av[c] * thb; bt0_[c] -= av[c] * th0; }
           return;
         }
-        const double t1 = (sigmu - c1) * rs1, t2 = (sigmu - c2) * rs2;
+        const double t1 = (sigmu - om * c1) * rs1, t2 = (sigmu - om * c2) * rs2;
         const double rhs_xi = -hw + t1 + t2;
         const double dxi = (rhs_xi - w1 * adz) * rw;
         const double ds1 = adz + dxi, ds2 = dxi;
-        const double dl1 = -l1 + (sigmu - c1) * rs1 - w1 * ds1, dl2 = -l2 + (sigmu - c2) * rs2 - w2 * ds2;
+        const double dl1 = -l1 + t1 - w1 * ds1, dl2 = -l2 + t2 - w2 * ds2;
         qp = fmax(qp, fmax(-ds1 * rs1, -ds2 * rs2)); upd_d(dl1, l1); upd_d(dl2, l2);
         st_na(ws.dxi + o, dxi); st_na(ws.dl1 + o, dl1); st_na(ws.dl2 + o, dl2);
       };
-      auto hinge_PS_range = [&](int k, const double* w, const double* da, const double* dz, double* bta_, double* btb_) {
+      auto hinge_PS_range = [&](int k, const double* w, const double* da, const double* dz, double* bta_, double* btb_, double* bt0_) {
         for (int h0 = h_lo; h0 < h_hi; h0 += HINGE_CHUNK) {
           prefetch_hinges(h0, false);
           HingeData<D> hb[HINGE_CHUNK];
@@ -1619,26 +1624,26 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge(h0 + c, k, ws.s);
 #pragma unroll
           for (int c = 0; c < HINGE_CHUNK; ++c)
-            if (hb[c].on) hinge_PS(h0 + c, hb[c], k, w, da, dz, bta_, btb_);
+            if (hb[c].on) hinge_PS(h0 + c, hb[c], k, w, da, dz, bta_, btb_, bt0_);
         }
       };
       {
         // helper groups: their share of stage kt's hinge rows (P: partial rhs pieces to the stage's owner)
-        double ph[2 * D];
+        double ph[3 * D];
 #pragma unroll
-        for (int i = 0; i < 2 * D; ++i) ph[i] = 0.0;
+        for (int i = 0; i < 3 * D; ++i) ph[i] = 0.0;
         if (helper && kt > 0 && kt < K - 1) {
           double wl[D], dal[D], dzl[D];     // position and the two directions' position parts, once
 #pragma unroll
           for (int c = 0; c < D; ++c) { wl[c] = Wl[kt * NSP + c]; dal[c] = dWal[kt * NSP + c]; dzl[c] = P ? 0.0 : dWl[kt * NSP + c]; }
-          hinge_PS_range(kt, wl, dal, dzl, ph, ph + D);
+          hinge_PS_range(kt, wl, dal, dzl, ph, ph + D, ph + 2 * D);
           if (P && grp > 0) {
             double* hs = HS + ((size_t)(grp - 1) * K + kt) * HSW;
 #pragma unroll
-            for (int i = 0; i < 2 * D; ++i) hs[i] = ph[i];
+            for (int i = 0; i < 3 * D; ++i) hs[i] = ph[i];
           }
         }
-        if (P) deposit_remote(std::integral_constant<int, 2 * D>{}, ph);
+        if (P) deposit_remote(std::integral_constant<int, 3 * D>{}, ph);
       }
       for (int k = tid; k < K; k += nthr) {
         const double* w = W + k * NSP;
@@ -1743,27 +1748,28 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
 #pragma unroll
             for (int j = 0; j < NU; ++j) { n2 += w[NX + j] * w[NX + j]; uda += w[NX + j] * da[NX + j]; udz += w[NX + j] * dz[NX + j]; }
             double ta = 0.0, tb = 0.0;
-            row(ws.s.lP[o], 0.5 * (n2 - sc.v_max * sc.v_max), uda, P ? 0.0 : udz, ta, tb, DLR(Dm::R_V), ws.s.sB + k, &dsb);
+            double t0 = 0.0;
+            row(ws.s.lP[o], 0.5 * (n2 - sc.v_max * sc.v_max), uda, P ? 0.0 : udz, ta, tb, DLR(Dm::R_V), ws.s.sB + k, &dsb, &t0);
             if (P) {
 #pragma unroll
-              for (int j = 0; j < NU; ++j) { bta[NX + j] += ta * w[NX + j]; btb[NX + j] += tb * w[NX + j]; }
+              for (int j = 0; j < NU; ++j) { bta[NX + j] += ta * w[NX + j]; btb[NX + j] += tb * w[NX + j]; BT0(NX + j) += t0 * w[NX + j]; }
             }
           }
-          hinge_PS_range(k, w, da, dz, bta, btb);
+          hinge_PS_range(k, w, da, dz, bta, btb, bt0);
         }
         if (P) {
-          // gradient of the smooth cost terms: independent of sigma mu
+          // gradient of the smooth cost terms: independent of sigma mu and of the second-order weight
 #pragma unroll
           for (int c = 0; c < D; ++c) {
             const double ql = qlin ? qlin[(size_t)c * K + k] * sc.cs : 0.0;
-            btb[c] += sc.qrho * w[c] + ql;
+            BT0(c) += sc.qrho * w[c] + ql;
           }
           if (game) {
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
               double g, cv, ob;
               game_terms(k, i, w, g, cv, ob);
-              btb[i] += g;
+              BT0(i) += g;
             }
           }
         }
@@ -1796,11 +1802,18 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           sg = fmin(fmax(sg, 0.0), 1.0);
           const double smu = sg * sg * sg * gl[44];
           gl[43] = smu;
+          // Mehrotra's second-order term ds_a dl_a presumes a full affine step; after a short one it points the corrector at products
+          // the iterate cannot reach.  It is weighed by om = min(alpha_p, alpha_d) of the affine step (oracle/ipm_struct.py: 23 % fewer
+          // iterations over 256 sub-problems of the bench scenes together with the step fraction of pass S and mu0 = 1e-3).
+          const double om = fmin(ap, ad);
+          gl[56] = om;
           // border part of the corrector's right-hand side
-          double bg[4] = {fma(smu, red[11], red[12]), fma(smu, red[5], red[8]), fma(smu, red[6], red[9]), fma(smu, red[7], red[10])};
+          double bg[4] = {fma(smu, red[11], om * red[12]), fma(smu, red[5], om * red[8]), fma(smu, red[6], om * red[9]),
+                          fma(smu, red[7], om * red[10])};
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             const double s = gl[12 + r], l = gl[15 + r], rp = gl[50 + r];
+            gl[53 + r] *= om;
             const double tau = (smu - gl[53 + r] + l * rp) * rcp_fast(s);
 #pragma unroll
             for (int i = 0; i < 4; ++i) bg[i] += gG(r, i) * tau;
@@ -1813,7 +1826,7 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
         __syncthreads();
         // own-stage + interval pieces of the corrector's right-hand side, now that sigma mu is known
         {
-          const double smu = gl[43];
+          const double smu = gl[43], om = gl[56];
           for (int k = tid; k < K; k += nthr) {
             const bool fr = (k > 0 && k < K - 1);
             if (!fr) continue;
@@ -1821,18 +1834,18 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
             const double* s0 = ST2 + (size_t)k * Dm::ST2;
             const double* s1 = ST2 + (size_t)(k - 1) * Dm::ST2;
 #pragma unroll
-            for (int i = 0; i < NX; ++i) { ek[i] = fma(smu, s0[i], dW[k * NSP + i]); ekm[i] = fma(smu, s1[i], dW[(k - 1) * NSP + i]); }
+            for (int i = 0; i < NX; ++i) { ek[i] = fma(smu, s0[i], om * dW[k * NSP + i]); ekm[i] = fma(smu, s1[i], om * dW[(k - 1) * NSP + i]); }
             JpT<Dm>(JAC + (size_t)k * NJ, ek, t);
             JnT<Dm>(JAC + (size_t)(k - 1) * NJ, ekm, t2);
             if (NSLOT > 0) {
               for (int g = 0; g < NSLOT; ++g) {
                 const double* hs = HS + ((size_t)g * K + k) * HSW;
 #pragma unroll
-                for (int c = 0; c < D; ++c) { bta[c] += hs[c]; btb[c] += hs[D + c]; }
+                for (int c = 0; c < D; ++c) { bta[c] += hs[c]; btb[c] += hs[D + c]; BT0(c) += hs[2 * D + c]; }
               }
             }
 #pragma unroll
-            for (int i = 0; i < NS; ++i) btb[i] = -(fma(smu, bta[i], btb[i]) + t[i] + t2[i]);
+            for (int i = 0; i < NS; ++i) btb[i] = -(fma(smu, bta[i], fma(om, btb[i], BT0(i))) + t[i] + t2[i]);
           }
           __syncthreads();            // every thread has read its neighbour's staging out of dW
           for (int k = tid; k < K; k += nthr) {
@@ -1902,7 +1915,10 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
           }
           double ap = 1.0 / qpm, ad = 1.0 / qdm;
           if (coupled) { ap = ad = fmin(ap, ad); }
-          ap = fmin(1.0, 0.999 * ap); ad = fmin(1.0, 0.999 * ad);
+          // fraction of the way to the boundary: 0.999 while the centring target is large, up to 1 - 1e-6 as it vanishes (the
+          // payload-free form of Mehrotra's step-to-boundary rule: same iteration counts on the twin as the full rule)
+          const double sf = fmin(0.999999, fmax(0.999, 1.0 - 1000.0 * sigmu));
+          ap = fmin(1.0, sf * ap); ad = fmin(1.0, sf * ad);
           gl[41] = ap; gl[42] = ad;
           if (!nan_step) {
             // the globals move now; the stage variables below; the row state in the next residual pass

@@ -63,7 +63,8 @@ def spd_inverse_frozen(Dj, piv_tol=1e-12, reg_rel=0.0):
 
 class StructIPM:
     def __init__(self, p: spb.Params, mu0=10.0, max_iter=60, eps_gap=1e-8, eps_feas=1e-9, verbose=False, linalg="cr", step_frac=0.999, uncapped=False,
-                 gondzio=0, g_thresh=0.5, g_delta=0.3):
+                 gondzio=0, g_thresh=0.5, g_delta=0.3, weigh_second_order=True, adaptive_step_frac=True):
+        self.weigh_second_order, self.adaptive_step_frac = bool(weigh_second_order), bool(adaptive_step_frac)
         # gondzio > 0: EXPERIMENT, not in the kernel: up to `gondzio` centrality correctors after a Mehrotra step whose
         # min(alpha_p, alpha_d) < g_thresh; n_solves counts the linear solves (2 per iteration + 1 per corrector tried)
         self.gondzio, self.g_thresh, self.g_delta, self.n_solves = int(gondzio), float(g_thresh), float(g_delta), 0
@@ -269,7 +270,10 @@ class StructIPM:
                 t = (v + ap * dv) * (l + ad * dl_)
                 comp_aff += (t * mk).sum() if mk is not None else t.sum()
             sg = (comp_aff / comp) ** 3
-            cc = [dv * dl_ for dv, dl_ in zip(dS, dL)]
+            # Mehrotra's second-order term presumes a full affine step; it is weighed by om = min(alpha_p, alpha_d) of the affine step
+            # (round 2; on 256 sub-problems of the bench scenes, together with the step fraction below and mu0 = 1e-3: 10.4 -> 7.9 iterations)
+            om = min(ap, ad) if self.weigh_second_order else 1.0
+            cc = [om * dv * dl_ for dv, dl_ in zip(dS, dL)]
             dW, dg, dxi, dS, dL = newton(sg * mu, *cc)
             cap = 1e300 if self.uncapped else 1.0
             ap, ad = maxstep(S, dS, cap), maxstep(L, dL, cap)
@@ -296,7 +300,9 @@ class StructIPM:
                 if ap_g + ad_g <= 1.01 * (ap + ad):
                     break
                 (dW, dg, dxi, dS, dL), ap, ad, cc = cand, ap_g, ad_g, cc_g
-            ap, ad = min(1.0, self.step_frac * ap), min(1.0, self.step_frac * ad)
+            # fraction of the way to the boundary: step_frac while the centring target is large, up to 1 - 1e-6 as it vanishes
+            sf = min(0.999999, max(self.step_frac, 1.0 - 1000.0 * sg * mu)) if self.adaptive_step_frac else self.step_frac
+            ap, ad = min(1.0, sf * ap), min(1.0, sf * ad)
             W = W + ap * dW; sig += ap * dg[0]; t_nu += ap * dg[1]; t_x += ap * dg[2]; t_u += ap * dg[3]
             xi = xi + ap * np.where(hfree, dxi, 0.0)
             # rows of the fixed stages are placeholders (the kernel never touches them): keep them frozen
