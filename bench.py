@@ -179,7 +179,7 @@ def run_ours(args, rank, world, local_rank):
     from scvx_b200 import _lib
     from scvx_b200.batch import BatchedSCvx, PipelinedSCvx
 
-    lanes = int(os.environ.get("SCVX_BENCH_LANES", "8"))
+    lanes = int(os.environ.get("SCVX_BENCH_LANES", "16"))
     # per-agent start of the barrier parameter from the previous solve's iteration count (scvx_mu0_from_iters): every sub-problem
     # is still solved to the same tolerance (solver_status_optimal_frac), ~15 % fewer interior-point iterations
     adaptive = bool(int(os.environ.get("SCVX_BENCH_ADAPTIVE_MU0", "1")))
@@ -250,6 +250,7 @@ def run_ours(args, rank, world, local_rank):
             X0 = torch.cat([st[0] for st in P.state]).cpu(); U0 = torch.cat([st[1] for st in P.state]).cpu()
             host["X"].copy_(X0); host["U"].copy_(U0); host["sigma"].fill_(1.0); host["tr"].fill_(100.0)
             P.run_host(host, warm)
+            P.build_lane_host_graphs(host)  # per lane: H2D copies + the step's kernels + D2H copies as one graph on the lane's stream
         else:
             P.run(warm)
             P.build_lane_graphs()          # one CUDA graph per lane (its launches of a step), replayed on the lane's stream
@@ -258,7 +259,7 @@ def run_ours(args, rank, world, local_rank):
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         if host_api:
-            P.run_host(host, steps)
+            P.run_host_lane_graphs(host, steps)
         else:
             P.run_lane_graphs(steps, keep_history=False)
         b_.record(stream)

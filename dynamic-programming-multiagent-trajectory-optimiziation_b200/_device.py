@@ -208,13 +208,14 @@ class SubproblemWorkspace:
         self.objective = torch.empty(n, dtype=F64, device=device)
         self.status = torch.empty(n, dtype=torch.int32, device=device)
         self.iters = torch.empty(n, dtype=torch.int32, device=device)
+        self.retry_list = torch.zeros(n + 1, dtype=torch.int32, device=device)      # scratch of the retry pass
 
 
 def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_radius, x_init, x_final, pos_lo,
                      pos_hi, v_max, w_max, obs_a, obs_b, weight_nu, weight_slack, weight_sigma,
                      col_a=None, col_b=None, col_mask=None, quad_rho=None, lin_p=None, weight_col=1e5,
                      max_iter=0, norm1_induced=True, quad_diag=None, lin_w=None, quad_pair=None, fix_sigma=False,
-                     block_order=None, mu0=None, active=None):
+                     block_order=None, mu0=None, active=None, retry_failed=False):
     """SCProblem.solve / AgentSolver.solve for a batch (sc_problem.py:15-105, agent_solver.py:43-117).
     Results land in the workspace's output tensors."""
     a = SolveArgs()
@@ -240,6 +241,8 @@ def solve_subproblem(ws: SubproblemWorkspace, mats, X_ref, U_ref, sigma_ref, tr_
     a.block_order = P(block_order)
     a.mu0 = P(mu0)
     a.active = P(active)
+    a.retry_failed = 1 if retry_failed else 0
+    a.retry_list = ptr(ws.retry_list) if retry_failed else None
     a.weight_nu, a.weight_slack, a.weight_sigma, a.weight_col = float(weight_nu), float(weight_slack), float(weight_sigma), float(weight_col)
     a.X, a.U, a.nu, a.sigma = ptr(ws.X), ptr(ws.U), ptr(ws.nu), ptr(ws.sigma)
     a.s_prime = ptr(ws.s_prime) if ws.M else None

@@ -36,7 +36,7 @@ class SolveArgs(ctypes.Structure):
         ("objective", _c_dp), ("status", _c_dp), ("iters", _c_dp),
         ("workspace", _c_dp), ("workspace_bytes", ctypes.c_ulonglong),
         ("quad_diag", _c_dp), ("lin_w", _c_dp), ("quad_pair", _c_dp), ("fix_sigma", _c_int), ("block_order", _c_dp), ("mu0", _c_dp),
-        ("active", _c_dp),
+        ("active", _c_dp), ("retry_failed", _c_int), ("retry_list", _c_dp),
     ]
 
 

@@ -81,6 +81,7 @@ class BatchedSCvx:
         # adaptive_mu0: warm sub-problems start at a small barrier parameter (MU0_POLICY) instead of the cold default 10
         self.adaptive_mu0 = bool(adaptive_mu0)
         self.mu0_policy = MU0_POLICY      # (easy_max_iters, mu0_easy, mu0_hard) of scvx_mu0_from_iters
+        self.retry_stranded = True        # warm solves that strand from the small start are re-solved cold in the same step
         self._mu0 = None
         b = self.batch
         self.K, self.max_iter, self.tr_radius0, self.conv_tol = K, max_iter, tr_radius0, conv_tol
@@ -111,6 +112,13 @@ class BatchedSCvx:
                                  b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
                                  self.weight_sigma, max_iter=self.ipm_max_iter, block_order=self._order, mu0=self._mu0,
                                  active=active)
+        if self._mu0 is not None and self.retry_stranded:
+            # retry pass: the few warm solves that stranded from the small barrier start (status != optimal) again from the cold one;
+            # every other block returns at once
+            _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
+                                     b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
+                                     self.weight_sigma, max_iter=self.ipm_max_iter, active=active, retry_failed=True)
+            self.launches += 1
         if solver_events is not None:
             solver_events[1].record(torch.cuda.current_stream())
         self._order = _device.order_by_iters(self.ws.iters, out=self._order_buf)
@@ -379,14 +387,54 @@ class PipelinedSCvx:
         main.synchronize()
         return host
 
+    def _host_step_of_lane(self, host, eng, d, a, c):
+        for k in ("X", "U", "sigma", "tr", "active"):
+            d[k].copy_(host[k][a:c], non_blocking=True)
+        eng.iterate(d["X"], d["U"], d["sigma"], d["tr"], d["active"], d["metrics"])
+        for k in ("X", "U", "sigma", "tr", "active", "metrics"):
+            host[k][a:c].copy_(d[k], non_blocking=True)
+
     def _enqueue_host_step(self, host):
         for eng, st, d, (a, c) in zip(self.engines, self.streams, self._dbuf, self.bounds):
             with torch.cuda.stream(st):
-                for k in ("X", "U", "sigma", "tr", "active"):
-                    d[k].copy_(host[k][a:c], non_blocking=True)
-                eng.iterate(d["X"], d["U"], d["sigma"], d["tr"], d["active"], d["metrics"])
-                for k in ("X", "U", "sigma", "tr", "active", "metrics"):
-                    host[k][a:c].copy_(d[k], non_blocking=True)
+                self._host_step_of_lane(host, eng, d, a, c)
+
+    def build_lane_host_graphs(self, host):
+        """One CUDA graph PER LANE holding one host-buffer step of that lane: the H2D copies of its slice of the pinned host arrays
+        (memcpy nodes), the step's kernels and the D2H copies.  Replayed on the lane's own stream by `run_host_lane_graphs`, the
+        lanes stay independent (as in `build_lane_graphs`) and the host issues n_lanes graph launches per step instead of
+        ~20 x n_lanes copies and kernel launches through Python -- which is what bounds `run_host` beyond a few lanes."""
+        if any(e._order is None for e in self.engines) or any(e.adaptive_mu0 and e._mu0 is None for e in self.engines):
+            self.run_host(host, 1)
+        torch.cuda.current_stream(self.device).synchronize()
+        self._hlgraphs, self._hl_host = [], host
+        launches0 = self.launches
+        for eng, st, d, (a, c) in zip(self.engines, self.streams, self._dbuf, self.bounds):
+            g = torch.cuda.CUDAGraph()
+            st.synchronize()
+            with torch.cuda.graph(g, stream=st):
+                self._host_step_of_lane(host, eng, d, a, c)
+            self._hlgraphs.append(g)
+        self._hl_launches = self.launches - launches0
+        for e in self.engines:
+            e.launches = 0
+        self._launch_base = launches0
+        return self
+
+    def run_host_lane_graphs(self, host, n_steps=1):
+        """`run_host` by replaying the lane graphs of `build_lane_host_graphs` (same host arrays): returns when every lane's
+        result of the last step is on the host."""
+        if host is not self._hl_host:
+            raise ValueError("PipelinedSCvx.run_host_lane_graphs: the graphs were captured on other host buffers")
+        main = self._fork()
+        for _ in range(n_steps):
+            for g, st in zip(self._hlgraphs, self.streams):
+                with torch.cuda.stream(st):
+                    g.replay()
+            self._launch_base += self._hl_launches
+        self._join(main)
+        main.synchronize()
+        return host
 
     def build_host_graph(self, host):
         """`run_host(host, 1)` as one CUDA graph: per lane the H2D copies of its slice, the step's kernels and the D2H copies

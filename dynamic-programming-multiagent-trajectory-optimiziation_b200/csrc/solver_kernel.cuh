@@ -598,7 +598,10 @@ __device__ __forceinline__ constexpr double gG(int r, int i) {
 //    same barriers and reductions and nothing else -- except the hinge shares: the C x G hinge groups of the cluster split a
 //    stage's rows, remote groups read the stage variables from the leader's shared memory (distributed shared memory) and
 //    deposit their partial sums there; block reductions that carry hinge statistics are completed across the cluster.
-template <class M, bool JSM, int G, int C>
+// RETRY: the retry pass over a compact list (a.retry_list: count, then the ids of the agents whose first solve failed), a few
+// blocks that walk the list -- a full-grid retry launch was measured to cost 3.5 % of a step just cycling 128 blocks that return
+// at once through block slots of 115 KB each; its main-path instantiation (RETRY = false) carries no loop.
+template <class M, bool JSM, int G, int C, bool RETRY>
 __global__ void __launch_bounds__(G == 1 ? SOLVER_MAX_THREADS : 128 * G, 1)
 ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_feas, size_t jac_ws_offset) {
   using Dm = Dims<M>;
@@ -608,19 +611,22 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   namespace cg = cooperative_groups;
   const int rank = (C > 1) ? (int)cg::this_cluster().block_rank() : 0;
   const bool leader = (rank == 0);
-  const int unit = (int)blockIdx.x / C;                       // one agent per cluster
-  const int K = a.K, agent = a.block_order ? a.block_order[unit] : unit, nthr = blockDim.x;
+  int unit = (int)blockIdx.x / C;                             // one agent per cluster
+next_unit:
+  if (RETRY && unit >= a.retry_list[0]) return;               // uniform over the block (and the cluster)
+  const int K = a.K, agent = RETRY ? a.retry_list[1 + unit] : (a.block_order ? a.block_order[unit] : unit), nthr = blockDim.x;
   const int htid = threadIdx.x;                                // index of this thread among its block's hinge workers
   const int tid = leader ? htid : htid + (1 << 20);            // owner-thread index: out of every loop's range on a helper block
   auto CSYNC = [&]() { if (C > 1) cg::this_cluster().sync(); };
   if (a.active && !a.active[agent]) {        // the agent's outer loop has converged: nothing to solve (uniform over the cluster)
-    if (threadIdx.x == 0 && leader) a.iters[agent] = 0;
+    if (threadIdx.x == 0 && leader && !a.retry_failed) a.iters[agent] = 0;
     return;
   }
+  if (!RETRY && a.retry_failed && a.status[agent] == SCVX_ST_OPTIMAL) return;      // full-grid retry pass: only the failed agents
   const int Mobs = a.M, NH = a.M + a.n_nbr;
   // start value of the barrier parameter: per agent when the caller provides one (scvx_mu0_from_iters), else the default
-  const double mu0_agent = a.mu0 ? a.mu0[agent] : 0.0;
-  const double mu0 = (mu0_agent > 0.0) ? mu0_agent : mu0_default;
+  const double mu0_agent = (a.mu0 && C == 1) ? a.mu0[agent] : 0.0;      // (cluster launches always start cold)
+  double mu0 = (mu0_agent > 0.0) ? mu0_agent : mu0_default;
 
   extern __shared__ __align__(16) double smem[];
   PHASE_INIT();
@@ -860,6 +866,29 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
     }
   }
   __syncthreads();
+  // A start below the default is for WARM problems only.  Where the start point violates a hinge row -- the trajectory runs through
+  // an obstacle of the new linearisation -- that pair's closed-form start carries a multiplier of the full penalty weight which no
+  // small plain-row multiplier balances: the dual residual starts ~1e5 x mu0 and the iteration strands on short dual steps (twin:
+  // 40-59 iterations against 15-27 from the cold start on the seven stranded sub-problems of tools/dump_stranded.py).  Such
+  // problems start cold.
+  if (C == 1 && mu0 < mu0_default) {
+    double vm[1] = {-1e300};
+    if (kt > 0 && kt < K - 1) {
+      double w[D];
+#pragma unroll
+      for (int c = 0; c < D; ++c) w[c] = W[kt * NSP + c];
+      for (int h = h_lo; h < h_hi; ++h) {
+        if (!hinge_on(h)) continue;
+        double ap = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) ap += hinge_a(h, c, kt) * w[c];
+        vm[0] = fmax(vm[0], hinge_b(h, kt) - ap);
+      }
+    }
+    const int opv[1] = {2};
+    block_reduce<1>(vm, opv, red);
+    if (red[0] > 1e-6) mu0 = mu0_default;
+  }
   {
     // t_nu, t_x, t_u from maxima over stages
     const double sig0 = fix_sig ? sc.sig_ref : fmax(sc.sig_ref, fmin(1e-2, sc.r_tr / 16.0));
@@ -979,7 +1008,9 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   PHASE(0);
   const double inv_n_rows = 1.0 / n_rows;
   int status = SCVX_ST_MAXITER, it = 0;
-  const int max_iter = a.max_iter > 0 ? a.max_iter : 80;
+  // a start below the default that has not converged after SMALL_START_CAP iterations gives up (the caller's retry pass solves it cold)
+  constexpr int SMALL_START_CAP = 40;
+  const int max_iter = (mu0 < mu0_default) ? min(a.max_iter > 0 ? a.max_iter : 80, SMALL_START_CAP) : (a.max_iter > 0 ? a.max_iter : 80);
 
   // =================================================================================================
   // Three row passes per iteration.  R: the pending step is applied to the row state, then residuals + Newton matrix staging +
@@ -2025,7 +2056,25 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   }
   CSYNC();                                  // no block of the cluster leaves while another may still read its shared memory
   PHASE(19);
+  if (RETRY) {                              // next entry of the failed list
+    __syncthreads();
+    unit += (int)gridDim.x / C;
+    goto next_unit;
+  }
 }
+
+// Compact list of the agents a retry pass has to solve: list[0] = count, list[1..] = their ids (any order).
+static __global__ void __launch_bounds__(256) retry_list_kernel(int n, const int* __restrict__ status, const int* __restrict__ active,
+                                                        int* __restrict__ list) {
+  __shared__ int cnt;
+  if (threadIdx.x == 0) cnt = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (status[i] != SCVX_ST_OPTIMAL && (!active || active[i])) list[1 + atomicAdd(&cnt, 1)] = i;
+  __syncthreads();
+  if (threadIdx.x == 0) list[0] = cnt;
+}
+constexpr int RETRY_BLOCKS = 8;
 
 constexpr size_t SMEM_LIMIT = 227 * 1024;
 // Two blocks per SM need <= (228 KB - 2 x 1 KB reserved) / 2 each; keep the Jacobians in shared memory only if that holds
@@ -2074,7 +2123,19 @@ size_t solver_ws_total_doubles(int n_agents, int K, int NH) {
 
 template <class M, bool JSM, int G, int C>
 int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off) {
-  auto kern = ipm_kernel<M, JSM, G, C>;
+  if constexpr (G == 1 && C == 1) {
+    if (a.retry_failed && a.retry_list) {
+      // compact retry pass: list the failed agents, then a few blocks walk the list
+      auto rk = ipm_kernel<M, JSM, 1, 1, true>;
+      cudaError_t e2 = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFuncSetAttribute");
+      retry_list_kernel<<<1, 256, 0, st>>>(a.n_agents, a.status, a.active, a.retry_list);
+      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, 10.0, 1e-8, 1e-9, jac_off);
+      SCVX_CHECK_LAUNCH("scvx_solve_batched (retry)");
+      return SCVX_OK;
+    }
+  }
+  auto kern = ipm_kernel<M, JSM, G, C, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   if (C == 1) {
@@ -2090,7 +2151,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
     attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     e = cudaLaunchKernelEx(&cfg, kern, a, 10.0, 1e-8, 1e-9, jac_off);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx (cluster)");
+    if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx");
   }
   SCVX_CHECK_LAUNCH("scvx_solve_batched");
   return SCVX_OK;

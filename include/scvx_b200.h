@@ -204,6 +204,15 @@ typedef struct scvx_solve_args {
   /* Outer-loop activity flags (n_agents ints, NULL = all active): the block of an agent whose flag is 0 -- its outer loop has
    * converged (scvx_outer_update) -- returns at once, iters = 0, every other output keeps its previous value. */
   const int *active;
+  /* Retry pass.  A solve that starts below the default barrier parameter (mu0[i] < 10) and has not converged after 40
+   * interior-point iterations ends with SCVX_ST_MAXITER (1 in ~20 000 warm solves of the bench scenes strands like this; every one
+   * of them converges from the cold start).  Launch the same arguments again with retry_failed = 1 and mu0 = NULL: blocks of agents
+   * whose status is SCVX_ST_OPTIMAL return at once and leave every output alone, the others are solved from the cold start. */
+  int retry_failed;
+  /* Scratch of the retry pass: n_agents + 1 ints (count, then the ids of the failed agents).  With it the retry pass is a list
+   * kernel plus a launch of a few blocks that walk the list; NULL (or a launch with hinge groups / clusters) = a full-grid launch
+   * whose blocks of optimal agents return at once. */
+  int *retry_list;
 } scvx_solve_args;
 
 /* order[r] = index of the agent with the r-th LARGEST iters (ties by index): a longest-first launch order for the next solve */

@@ -141,6 +141,10 @@ class StructIPM:
         t_x = np.abs(W[:, :nx] - Wref[:, :nx]).sum(axis=1).max() + r_tr / 4
         t_u = np.abs(W[:, nx:] - Wref[:, nx:]).sum(axis=1).max() + r_tr / 4
         mu0 = self.mu0
+        # a start below the default is for warm problems only: where the start point violates a hinge row the solve starts cold
+        # (the kernel's rule; see csrc/solver_kernel.cuh)
+        if mu0 < 10.0 and self.nh and (self.hb - np.einsum("hdk,dk->hk", self.ha, W[:, :d].T))[:, 1:-1].max() > 1e-6:
+            mu0 = 10.0
 
         def plain_slacks(W, sig, t_nu, t_x, t_u):
             """h - G z for every plain row family (positive = satisfied)."""

@@ -42,6 +42,31 @@ def test_graph_replay_is_identical_to_eager_lanes(cuda):
         assert P.launches == ref.launches
 
 
+def test_host_lane_graphs_are_identical_to_eager_host_steps(cuda):
+    """`build_lane_host_graphs` captures, per lane, the H2D copies + the step's kernels + the D2H copies; replaying them gives the
+    same host arrays as the eager `run_host`, bit for bit (adaptive barrier start and retry pass included)."""
+    from scvx_b200.batch import PipelinedSCvx
+    _, models = _scene_models(10, 6)
+    K, n_it = 30, 6
+
+    def fresh():
+        P = PipelinedSCvx(models, K, n_lanes=3, max_iter=n_it, adaptive_mu0=True).start()
+        host = P.make_host_buffers()
+        host["X"].copy_(torch.cat([st[0] for st in P.state]).cpu()); host["U"].copy_(torch.cat([st[1] for st in P.state]).cpu())
+        host["sigma"].fill_(1.0); host["tr"].fill_(100.0)
+        return P, host
+
+    P, want = fresh()
+    P.run_host(want, n_it)
+    Q, got = fresh()
+    Q.run_host(got, 2)
+    Q.build_lane_host_graphs(got)
+    Q.run_host_lane_graphs(got, n_it - 2)
+    for key in ("X", "U", "sigma", "tr", "active", "metrics"):
+        assert torch.equal(got[key], want[key]), key
+    assert Q.launches == P.launches
+
+
 def test_adaptive_barrier_start_keeps_every_subproblem_optimal(cuda):
     """adaptive_mu0: agents whose previous solve was short start the next one at mu = 0.1.  Every sub-problem of 6 outer
     iterations still matches the exact LP on the loop's own parameters to 1e-7 (the start changes WHICH minimiser of a
@@ -73,6 +98,44 @@ def test_adaptive_barrier_start_keeps_every_subproblem_optimal(cuda):
                     assert e["viol"] <= 1e-8 and abs(e["obj"] - r["obj"]) <= 1e-7 * abs(r["obj"]), (i, e["obj"], r["obj"])
         totals[adaptive] = total
     assert totals[True] <= totals[False]
+
+
+def test_retry_pass_solves_only_the_failed_agents(cuda):
+    """scvx_solve_args.retry_failed: a second launch of the same arguments re-solves, from the cold start, exactly the agents whose
+    status is not optimal; every other block returns at once and leaves all of its outputs (iters included) alone.  A solve from a
+    small barrier start gives up after 40 iterations instead of running to the cap."""
+    from scvx_b200 import _device
+    from scvx_b200.batch import BatchedSCvx
+    _, models = _scene_models(5, 33, M=6)
+    K = 40
+    eng = BatchedSCvx(models, K)
+    b, ws = eng.batch, eng.ws
+    X, U = b.initial_trajectories()
+    n = b.n
+    sig = torch.ones(n, dtype=torch.float64, device=cuda); tr = torch.full((n,), 100.0, dtype=torch.float64, device=cuda)
+    _device.foh(b.model_id, X, U, sig, 0, out=eng.mats)
+    _device.linearize_obstacles(b.model_id, X, b.obs_c, b.obs_clear, out=(eng.obs_a, eng.obs_b))
+
+    def solve(**kw):
+        _device.solve_subproblem(ws, eng.mats, X, U, sig, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi, b.v_max, b.w_max,
+                                 eng.obs_a, eng.obs_b, eng.weight_nu, eng.weight_slack, eng.weight_sigma, **kw)
+        torch.cuda.synchronize()
+        return {k: getattr(ws, k).clone() for k in ("X", "U", "nu", "sigma", "objective", "status", "iters")}
+
+    cold = solve()
+    assert (cold["status"] == 0).all()
+    cut = solve(max_iter=2)                       # every agent stops at the cap: status MAXITER, outputs of a half-done solve
+    assert (cut["status"] == 1).all() and (cut["iters"] == 2).all()
+    ws.status[0] = 0                              # pretend agent 0 had converged
+    again = solve(retry_failed=True)
+    for key in cold:
+        assert torch.equal(again[key][1:], cold[key][1:]), key          # re-solved from the cold start: the cold solve, bit for bit
+        if key != "status":
+            assert torch.equal(again[key][0], cut[key][0]), key         # agent 0: untouched
+    # small start: either converged, or gave up at 40 iterations (never the full cap of 80)
+    small = solve(mu0=torch.full((n,), 1e-3, dtype=torch.float64, device=cuda))
+    assert ((small["status"] == 0) | (small["iters"] <= 40)).all()
+    np.testing.assert_allclose(small["objective"].cpu().numpy(), cold["objective"].cpu().numpy(), rtol=1e-7)
 
 
 def _si_crowd(n_nbr, K, n_problems, seed):

@@ -22,7 +22,7 @@ if len(sys.argv) > 1:
 for pol in POLICIES:
     if pol is not None:
         B.MU0_POLICY = pol
-    P = B.PipelinedSCvx(models, 100, n_lanes=8, max_iter=23, adaptive_mu0=pol is not None).start()
+    P = B.PipelinedSCvx(models, 100, n_lanes=int(os.environ.get('LANES', '8')), max_iter=23, adaptive_mu0=pol is not None).start()
     bad = 0
     for _ in range(3):
         P.run(1); torch.cuda.synchronize()

@@ -15,6 +15,7 @@ seed = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 scenes = bench.make_scenes(n, seed)
 models = [UnicycleModel(r_init=o.x_init, r_final=o.x_final, obstacles=[(list(c), r) for c, r in o.obstacles]) for o in scenes]
 eng = BatchedSCvx(models, 100, max_iter=iters, adaptive_mu0=(os.environ.get('SCVX_ADAPTIVE_MU0', '1') != '0'))
+eng.retry_stranded = os.environ.get('SCVX_RETRY', '1') != '0'
 out = eng.solve(early_exit=False)
 torch.cuda.synchronize()
 st = out["status"].cpu().numpy(); it = out["ipm_iters"].cpu().numpy(); met = out["metrics"].cpu().numpy()
