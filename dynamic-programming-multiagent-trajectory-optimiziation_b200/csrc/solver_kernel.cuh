@@ -603,7 +603,7 @@ __device__ __forceinline__ constexpr double gG(int r, int i) {
 // at once through block slots of 115 KB each; its main-path instantiation (RETRY = false) carries no loop.
 template <class M, bool JSM, int G, int C, bool RETRY>
 __global__ void __launch_bounds__(G == 1 ? SOLVER_MAX_THREADS : 128 * G, 1)
-ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_feas, size_t jac_ws_offset) {
+ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_feas, size_t jac_ws_offset, double om_floor, double sf_cap) {
   using Dm = Dims<M>;
   constexpr int NX = Dm::NX, NU = Dm::NU, D = Dm::D, NS = Dm::NS, NEX = Dm::NEX, NEU = Dm::NEU;
   constexpr int NSP = Dm::NSP, SD = Dm::SD, SR = Dm::SR, NJ = Dm::NJ, STG = Dm::STG, NPLAIN = Dm::NPLAIN;
@@ -1836,7 +1836,9 @@ next_unit:
           // Mehrotra's second-order term ds_a dl_a presumes a full affine step; after a short one it points the corrector at products
           // the iterate cannot reach.  It is weighed by om = min(alpha_p, alpha_d) of the affine step (oracle/ipm_struct.py: 23 % fewer
           // iterations over 256 sub-problems of the bench scenes together with the step fraction of pass S and mu0 = 1e-3).
-          const double om = fmin(ap, ad);
+          // (problems with one common step length -- quadratic cost or the ball row -- keep the full term: weighing it was measured
+          // to cost 15 % more iterations on config 4)
+          const double om = coupled ? 1.0 : fmax(fmin(ap, ad), om_floor);
           gl[56] = om;
           // border part of the corrector's right-hand side
           double bg[4] = {fma(smu, red[11], om * red[12]), fma(smu, red[5], om * red[8]), fma(smu, red[6], om * red[9]),
@@ -1948,7 +1950,7 @@ next_unit:
           if (coupled) { ap = ad = fmin(ap, ad); }
           // fraction of the way to the boundary: 0.999 while the centring target is large, up to 1 - 1e-6 as it vanishes (the
           // payload-free form of Mehrotra's step-to-boundary rule: same iteration counts on the twin as the full rule)
-          const double sf = fmin(0.999999, fmax(0.999, 1.0 - 1000.0 * sigmu));
+          const double sf = fmin(sf_cap, fmax(0.999, 1.0 - 1000.0 * sigmu));
           ap = fmin(1.0, sf * ap); ad = fmin(1.0, sf * ad);
           gl[41] = ap; gl[42] = ad;
           if (!nan_step) {
@@ -2123,6 +2125,9 @@ size_t solver_ws_total_doubles(int n_agents, int K, int NH) {
 
 template <class M, bool JSM, int G, int C>
 int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off) {
+  // experiment switches (defaults = the rules described at the tail of pass P / pass S): SCVX_OM_FLOOR=1 SCVX_SF_CAP=0.999 is plain Mehrotra
+  static const double om_floor = getenv("SCVX_OM_FLOOR") ? atof(getenv("SCVX_OM_FLOOR")) : 0.0;
+  static const double sf_cap = getenv("SCVX_SF_CAP") ? atof(getenv("SCVX_SF_CAP")) : 0.999999;
   if constexpr (G == 1 && C == 1) {
     if (a.retry_failed && a.retry_list) {
       // compact retry pass: list the failed agents, then a few blocks walk the list
@@ -2130,7 +2135,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
       cudaError_t e2 = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFuncSetAttribute");
       retry_list_kernel<<<1, 256, 0, st>>>(a.n_agents, a.status, a.active, a.retry_list);
-      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, 10.0, 1e-8, 1e-9, jac_off);
+      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, 10.0, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
       SCVX_CHECK_LAUNCH("scvx_solve_batched (retry)");
       return SCVX_OK;
     }
@@ -2139,7 +2144,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   if (C == 1) {
-    kern<<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off);
+    kern<<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off, om_floor, sf_cap);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.n_agents * C);
@@ -2150,7 +2155,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, a, 10.0, 1e-8, 1e-9, jac_off);
+    e = cudaLaunchKernelEx(&cfg, kern, a, 10.0, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx");
   }
   SCVX_CHECK_LAUNCH("scvx_solve_batched");

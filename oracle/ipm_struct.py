@@ -276,7 +276,8 @@ class StructIPM:
             sg = (comp_aff / comp) ** 3
             # Mehrotra's second-order term presumes a full affine step; it is weighed by om = min(alpha_p, alpha_d) of the affine step
             # (round 2; on 256 sub-problems of the bench scenes, together with the step fraction below and mu0 = 1e-3: 10.4 -> 7.9 iterations)
-            om = min(ap, ad) if self.weigh_second_order else 1.0
+            # (problems with one common step length -- quadratic cost, ball row -- keep the full term: weighing it costs them iterations)
+            om = min(ap, ad) if (self.weigh_second_order and not (self.qrho > 0 or self.ball)) else 1.0
             cc = [om * dv * dl_ for dv, dl_ in zip(dS, dL)]
             dW, dg, dxi, dS, dL = newton(sg * mu, *cc)
             cap = 1e300 if self.uncapped else 1.0

@@ -12,7 +12,7 @@ import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 
 KERNEL_REGEX = ("foh_rk4|integrate_|linearize_|ipm_kernel|outer_update|order_by_iters|consensus_kernel|lti_qp|sbar_|"
-                "slab_normals|warm_start|min_pair|min_obstacle|intersample|clearance_samples|cross_min|admm_prep|knn_select|radius_mask|mu0_from_iters")
+                "slab_normals|warm_start|min_pair|min_obstacle|intersample|clearance_samples|cross_min|admm_prep|knn_select|radius_mask|mu0_from_iters|retry_list")
 METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active,"
            "smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,"
            "smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,"
@@ -74,7 +74,7 @@ def scene(M):
 
 scenes = [scene(M) for _ in range(n)]
 models = [UnicycleModel(r_init=s0, r_final=s1, obstacles=ob) for s0, s1, ob in scenes]
-eng = BatchedSCvx(models, K, max_iter=4)
+eng = BatchedSCvx(models, K, max_iter=4, adaptive_mu0=True)      # with the warm barrier start: mu0 map, retry list, retry pass
 b = eng.batch
 X, U = b.initial_trajectories()
 sig = torch.ones(n, dtype=F64, device=dev); tr = torch.full((n,), 100.0, dtype=F64, device=dev)
