@@ -2128,6 +2128,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
   // experiment switches (defaults = the rules described at the tail of pass P / pass S): SCVX_OM_FLOOR=1 SCVX_SF_CAP=0.999 is plain Mehrotra
   static const double om_floor = getenv("SCVX_OM_FLOOR") ? atof(getenv("SCVX_OM_FLOOR")) : 0.0;
   static const double sf_cap = getenv("SCVX_SF_CAP") ? atof(getenv("SCVX_SF_CAP")) : 0.999999;
+  static const double mu0_def = getenv("SCVX_MU0_DEFAULT") ? atof(getenv("SCVX_MU0_DEFAULT")) : 10.0;
   if constexpr (G == 1 && C == 1) {
     if (a.retry_failed && a.retry_list) {
       // compact retry pass: list the failed agents, then a few blocks walk the list
@@ -2135,7 +2136,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
       cudaError_t e2 = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFuncSetAttribute");
       retry_list_kernel<<<1, 256, 0, st>>>(a.n_agents, a.status, a.active, a.retry_list);
-      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, 10.0, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
+      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, mu0_def, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
       SCVX_CHECK_LAUNCH("scvx_solve_batched (retry)");
       return SCVX_OK;
     }
@@ -2144,7 +2145,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   if (C == 1) {
-    kern<<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/10.0, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off, om_floor, sf_cap);
+    kern<<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/mu0_def, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off, om_floor, sf_cap);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.n_agents * C);
@@ -2155,7 +2156,7 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, a, 10.0, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
+    e = cudaLaunchKernelEx(&cfg, kern, a, mu0_def, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx");
   }
   SCVX_CHECK_LAUNCH("scvx_solve_batched");
