@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscvx_b200.so")
-SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "solver_unicycle.cu", "solver_si.cu", "lti_qp.cu", "utils.cu", "intersample.cu", "probe.cu", "user_model.cu", "admm_round.cu"]
+SOURCES = ["foh.cu", "linearize.cu", "solver.cu", "solver_unicycle.cu", "solver_si.cu", "solver_unicycle_fixed.cu", "solver_si_fixed.cu", "lti_qp.cu", "utils.cu", "intersample.cu", "probe.cu", "user_model.cu", "admm_round.cu"]
 OBJ_DIR = os.path.join(HERE, "build")          # object files (git-ignored); only the .so sits next to the package
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 

@@ -601,7 +601,12 @@ __device__ __forceinline__ constexpr double gG(int r, int i) {
 // RETRY: the retry pass over a compact list (a.retry_list: count, then the ids of the agents whose first solve failed), a few
 // blocks that walk the list -- a full-grid retry launch was measured to cost 3.5 % of a step just cycling 128 blocks that return
 // at once through block slots of 115 KB each; its main-path instantiation (RETRY = false) carries no loop.
-template <class M, bool JSM, int G, int C, bool RETRY>
+// KT: the number of nodes as a compile-time constant (0 = read a.K): every row-state / shared-memory address is then base + k + a
+// constant, which removes most of the integer arithmetic of the row passes (37 % of the executed instructions of the run-time-K
+// kernel were integer operations and register moves).  Instantiated for K = 100, the horizon of BASELINE configs 2-4.
+// MT: with KT, the number of obstacle rows per stage as a compile-time constant for the PLAIN sub-problem of SCProblem (-1 = run time):
+//     no inter-agent rows, no quadratic / linear / game terms, sigma free -- the launch checks that the arguments say so.
+template <class M, bool JSM, int G, int C, bool RETRY, int KT = 0, int MT = -1>
 __global__ void __launch_bounds__(G == 1 ? SOLVER_MAX_THREADS : 128 * G, 1)
 ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_feas, size_t jac_ws_offset, double om_floor, double sf_cap) {
   using Dm = Dims<M>;
@@ -614,7 +619,8 @@ ipm_kernel(scvx_solve_args a, double mu0_default, double eps_gap, double eps_fea
   int unit = (int)blockIdx.x / C;                             // one agent per cluster
 next_unit:
   if (RETRY && unit >= a.retry_list[0]) return;               // uniform over the block (and the cluster)
-  const int K = a.K, agent = RETRY ? a.retry_list[1 + unit] : (a.block_order ? a.block_order[unit] : unit), nthr = blockDim.x;
+  const int K = KT > 0 ? KT : a.K, agent = RETRY ? a.retry_list[1 + unit] : (a.block_order ? a.block_order[unit] : unit);
+  const int nthr = (KT > 0 && G == 1) ? ((KT + 31) / 32) * 32 : (int)blockDim.x;      // (the launch uses exactly this block size)
   const int htid = threadIdx.x;                                // index of this thread among its block's hinge workers
   const int tid = leader ? htid : htid + (1 << 20);            // owner-thread index: out of every loop's range on a helper block
   auto CSYNC = [&]() { if (C > 1) cg::this_cluster().sync(); };
@@ -623,7 +629,7 @@ next_unit:
     return;
   }
   if (!RETRY && a.retry_failed && a.status[agent] == SCVX_ST_OPTIMAL) return;      // full-grid retry pass: only the failed agents
-  const int Mobs = a.M, NH = a.M + a.n_nbr;
+  const int Mobs = (MT >= 0) ? MT : a.M, NH = (MT >= 0) ? MT : a.M + a.n_nbr;
   // start value of the barrier parameter: per agent when the caller provides one (scvx_mu0_from_iters), else the default
   const double mu0_agent = (a.mu0 && C == 1) ? a.mu0[agent] : 0.0;      // (cluster launches always start cold)
   double mu0 = (mu0_agent > 0.0) ? mu0_agent : mu0_default;
@@ -712,15 +718,16 @@ next_unit:
   sc.v_max = a.v_max[agent]; sc.w_max = a.w_max ? a.w_max[agent] : 0.0;
   sc.cs = 1.0 / fmax(fmax(a.weight_nu, a.weight_sigma), 1e-300);
   sc.c_sig = a.weight_sigma * sc.cs; sc.c_tnu = a.weight_nu * sc.cs;
-  sc.qrho = a.quad_rho ? a.quad_rho[agent] * sc.cs : 0.0;
+  constexpr bool PLAIN = (MT >= 0);
+  sc.qrho = (!PLAIN && a.quad_rho) ? a.quad_rho[agent] * sc.cs : 0.0;
   sc.hw_obs = a.weight_slack * sc.cs; sc.hw_col = a.weight_col * sc.cs;
-  const double* qlin = a.lin_p ? a.lin_p + (size_t)agent * D * K : nullptr;
+  const double* qlin = (!PLAIN && a.lin_p) ? a.lin_p + (size_t)agent * D * K : nullptr;
   // best-response terms (all absent for the plain problems): diagonal / linear / consecutive-difference quadratics
-  const double* qdiag = a.quad_diag ? a.quad_diag + (size_t)agent * NS : nullptr;
-  const double* qpair = a.quad_pair ? a.quad_pair + (size_t)agent * NS : nullptr;
-  const double* qlinw = a.lin_w ? a.lin_w + (size_t)agent * NS * K : nullptr;
+  const double* qdiag = (!PLAIN && a.quad_diag) ? a.quad_diag + (size_t)agent * NS : nullptr;
+  const double* qpair = (!PLAIN && a.quad_pair) ? a.quad_pair + (size_t)agent * NS : nullptr;
+  const double* qlinw = (!PLAIN && a.lin_w) ? a.lin_w + (size_t)agent * NS * K : nullptr;
   const bool game = qdiag || qpair || qlinw;
-  const bool fix_sig = a.fix_sigma != 0;
+  const bool fix_sig = !PLAIN && a.fix_sigma != 0;
   // gradient and curvature of the smooth extra cost at stage k, component i (scaled); obj: this stage's share of the value
   auto game_terms = [&](int k, int i, const double* w, double& grad, double& curv, double& obj) {
     grad = 0.0; curv = 0.0; obj = 0.0;
@@ -734,9 +741,9 @@ next_unit:
   };
   const double* obs_a = a.obs_a ? a.obs_a + (size_t)agent * Mobs * D * K : nullptr;
   const double* obs_b = a.obs_b ? a.obs_b + (size_t)agent * Mobs * K : nullptr;
-  const double* col_a = a.col_a ? a.col_a + (size_t)agent * a.n_nbr * D * K : nullptr;
-  const double* col_b = a.col_b ? a.col_b + (size_t)agent * a.n_nbr * K : nullptr;
-  const unsigned char* col_mask = a.col_mask ? a.col_mask + (size_t)agent * a.n_nbr : nullptr;
+  const double* col_a = (!PLAIN && a.col_a) ? a.col_a + (size_t)agent * a.n_nbr * D * K : nullptr;
+  const double* col_b = (!PLAIN && a.col_b) ? a.col_b + (size_t)agent * a.n_nbr * K : nullptr;
+  const unsigned char* col_mask = (!PLAIN && a.col_mask) ? a.col_mask + (size_t)agent * a.n_nbr : nullptr;
   const bool coupled = (sc.qrho > 0.0) || BALL || game;  // common primal/dual step length
 
   AgentPtrs ws;
@@ -1010,7 +1017,7 @@ next_unit:
   int status = SCVX_ST_MAXITER, it = 0;
   // a start below the default that has not converged after SMALL_START_CAP iterations gives up (the caller's retry pass solves it cold)
   constexpr int SMALL_START_CAP = 40;
-  const int max_iter = (mu0 < mu0_default) ? min(a.max_iter > 0 ? a.max_iter : 80, SMALL_START_CAP) : (a.max_iter > 0 ? a.max_iter : 80);
+  const int max_iter = (mu0 < mu0_default) ? min(a.max_iter > 0 ? a.max_iter : 120, SMALL_START_CAP) : (a.max_iter > 0 ? a.max_iter : 120);
 
   // =================================================================================================
   // Three row passes per iteration.  R: the pending step is applied to the row state, then residuals + Newton matrix staging +
@@ -2123,29 +2130,22 @@ size_t solver_ws_total_doubles(int n_agents, int K, int NH) {
   return tot;
 }
 
-template <class M, bool JSM, int G, int C>
-int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off) {
-  // experiment switches (defaults = the rules described at the tail of pass P / pass S): SCVX_OM_FLOOR=1 SCVX_SF_CAP=0.999 is plain Mehrotra
-  static const double om_floor = getenv("SCVX_OM_FLOOR") ? atof(getenv("SCVX_OM_FLOOR")) : 0.0;
-  static const double sf_cap = getenv("SCVX_SF_CAP") ? atof(getenv("SCVX_SF_CAP")) : 0.999999;
-  static const double mu0_def = getenv("SCVX_MU0_DEFAULT") ? atof(getenv("SCVX_MU0_DEFAULT")) : 10.0;
-  if constexpr (G == 1 && C == 1) {
-    if (a.retry_failed && a.retry_list) {
-      // compact retry pass: list the failed agents, then a few blocks walk the list
-      auto rk = ipm_kernel<M, JSM, 1, 1, true>;
-      cudaError_t e2 = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFuncSetAttribute");
-      retry_list_kernel<<<1, 256, 0, st>>>(a.n_agents, a.status, a.active, a.retry_list);
-      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, mu0_def, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
-      SCVX_CHECK_LAUNCH("scvx_solve_batched (retry)");
-      return SCVX_OK;
-    }
-  }
-  auto kern = ipm_kernel<M, JSM, G, C, false>;
+// launch parameters that do not depend on the problem (the rules at the tail of pass P / pass S, with their experiment switches:
+// SCVX_OM_FLOOR=1 SCVX_SF_CAP=0.999 is plain Mehrotra)
+struct IpmTuning { double mu0_def, om_floor, sf_cap; };
+inline IpmTuning ipm_tuning() {
+  static const IpmTuning t = {getenv("SCVX_MU0_DEFAULT") ? atof(getenv("SCVX_MU0_DEFAULT")) : 10.0,
+                              getenv("SCVX_OM_FLOOR") ? atof(getenv("SCVX_OM_FLOOR")) : 0.0,
+                              getenv("SCVX_SF_CAP") ? atof(getenv("SCVX_SF_CAP")) : 0.999999};
+  return t;
+}
+template <class Kern>
+int launch_ipm_kernel(Kern kern, int C, const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off) {
+  const IpmTuning t = ipm_tuning();
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
   if (C == 1) {
-    kern<<<a.n_agents, threads, smem, st>>>(a, /*mu0=*/mu0_def, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off, om_floor, sf_cap);
+    kern<<<a.n_agents, threads, smem, st>>>(a, t.mu0_def, /*eps_gap=*/1e-8, /*eps_feas=*/1e-9, jac_off, t.om_floor, t.sf_cap);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.n_agents * C);
@@ -2156,11 +2156,50 @@ int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int thr
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, a, mu0_def, 1e-8, 1e-9, jac_off, om_floor, sf_cap);
+    e = cudaLaunchKernelEx(&cfg, kern, a, t.mu0_def, 1e-8, 1e-9, jac_off, t.om_floor, t.sf_cap);
     if (e != cudaSuccess) return cuda_fail(e, "cudaLaunchKernelEx");
   }
   SCVX_CHECK_LAUNCH("scvx_solve_batched");
   return SCVX_OK;
+}
+
+// Instantiations with the sizes of the BASELINE configs as compile-time constants live in translation units of their own; same
+// code, results equal to round-off (the compiler contracts other multiply-add pairs once sizes and absent terms are constants)
+// (solver_unicycle_fixed.cu, solver_si_fixed.cu: they compile in parallel with the generic ones).  Returns IPM_NOT_FIXED when no
+// instantiation matches the arguments; the generic kernel runs then.  SCVX_NO_FIXED=1 switches them off (experiments / tests).
+constexpr int IPM_NOT_FIXED = 1;
+template <class M>
+int launch_ipm_fixed(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off, bool jsm, int G, int C);
+template <>
+int launch_ipm_fixed<Unicycle>(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off, bool jsm, int G, int C);
+template <>
+int launch_ipm_fixed<SingleIntegrator>(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off, bool jsm, int G, int C);
+// the plain sub-problem of SCProblem: obstacle rows only, no optional term
+inline bool ipm_args_plain(const scvx_solve_args& a) {
+  return a.n_nbr == 0 && !a.quad_rho && !a.lin_p && !a.quad_diag && !a.lin_w && !a.quad_pair && !a.fix_sigma && !a.col_a && !a.col_b && !a.col_mask;
+}
+
+template <class M, bool JSM, int G, int C>
+int launch_ipm_g(const scvx_solve_args& a, cudaStream_t st, size_t smem, int threads, size_t jac_off) {
+  if constexpr (G == 1 && C == 1) {
+    if (a.retry_failed && a.retry_list) {
+      // compact retry pass: list the failed agents, then a few blocks walk the list
+      const IpmTuning t = ipm_tuning();
+      auto rk = ipm_kernel<M, JSM, 1, 1, true>;
+      cudaError_t e2 = cudaFuncSetAttribute(rk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e2 != cudaSuccess) return cuda_fail(e2, "cudaFuncSetAttribute");
+      retry_list_kernel<<<1, 256, 0, st>>>(a.n_agents, a.status, a.active, a.retry_list);
+      rk<<<a.n_agents < RETRY_BLOCKS ? a.n_agents : RETRY_BLOCKS, threads, smem, st>>>(a, t.mu0_def, 1e-8, 1e-9, jac_off, t.om_floor, t.sf_cap);
+      SCVX_CHECK_LAUNCH("scvx_solve_batched (retry)");
+      return SCVX_OK;
+    }
+  }
+  const bool no_fixed = getenv("SCVX_NO_FIXED") != nullptr;      // (read per call: the tests switch it)
+  if (!no_fixed) {
+    const int r = launch_ipm_fixed<M>(a, st, smem, threads, jac_off, JSM, G, C);
+    if (r != IPM_NOT_FIXED) return r;
+  }
+  return launch_ipm_kernel(ipm_kernel<M, JSM, G, C, false>, C, a, st, smem, threads, jac_off);
 }
 
 inline int sm_count() {

@@ -100,6 +100,31 @@ def test_adaptive_barrier_start_keeps_every_subproblem_optimal(cuda):
     assert totals[True] <= totals[False]
 
 
+def test_fixed_size_kernels_agree_with_the_generic_one(cuda):
+    """`ipm_kernel` instantiated with K = 100 (and, for the plain sub-problem, M = 8) as compile-time constants -- the launch picks
+    these for the BASELINE sizes -- solves the same problems as the generic kernel (SCVX_NO_FIXED=1): same statuses, iteration
+    counts within one, optimal values equal to 1e-9 (the compiler contracts other multiply-add pairs: round-off, not bitwise)."""
+    import test_subproblem_gpu as T
+    rng = np.random.default_rng(5)
+    oms = [helpers.random_unicycle_scene(rng, 8) for _ in range(6)]
+    plain = []
+    for om in oms:
+        plain += [p for p, _ in helpers.make_problem_sequence(om, 100, 2)]
+    coupled = [T._admm_problem("unicycle", 5, 100, i, rng) for i in range(3)]           # K = 100 with inter-agent rows and quadratic terms
+    crowd = [T._admm_problem("single_integrator", 81, 100, i, rng) for i in range(2)]    # two hinge groups, cluster launch
+    for ps in (plain, coupled, crowd):
+        got = helpers.solve_batch_on_gpu(ps, cuda)
+        g = (got.objective.cpu().numpy().copy(), got.status.cpu().numpy().copy(), got.iters.cpu().numpy().copy())
+        os.environ["SCVX_NO_FIXED"] = "1"
+        try:
+            ref = helpers.solve_batch_on_gpu(ps, cuda)
+        finally:
+            os.environ.pop("SCVX_NO_FIXED", None)
+        assert (g[1] == 0).all() and (ref.status == 0).all()
+        np.testing.assert_allclose(g[0], ref.objective.cpu().numpy(), rtol=1e-9)
+        assert np.abs(g[2] - ref.iters.cpu().numpy()).max() <= 1
+
+
 def test_retry_pass_solves_only_the_failed_agents(cuda):
     """scvx_solve_args.retry_failed: a second launch of the same arguments re-solves, from the cold start, exactly the agents whose
     status is not optimal; every other block returns at once and leaves all of its outputs (iters included) alone.  A solve from a

@@ -1,6 +1,6 @@
 """Per-phase SM cycles of ipm_kernel (block 0).  Build first with
     SCVX_NVCC_EXTRA=-DSCVX_PHASE_TIMING python -m scvx_b200._build --force
-usage: python tools/phase_timing.py [n_agents] [outer_iters]"""
+usage: SCVX_NO_FIXED=1 python tools/phase_timing.py [n_agents] [outer_iters]      (the counters live in the generic kernels' translation unit)"""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
