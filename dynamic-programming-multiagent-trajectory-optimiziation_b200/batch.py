@@ -118,7 +118,7 @@ class BatchedSCvx:
             _device.solve_subproblem(self.ws, self.mats, X, U, sigma, tr, b.x_init, b.x_final, b.pos_lo, b.pos_hi,
                                      b.v_max, b.w_max, self.obs_a, self.obs_b, self.weight_nu, self.weight_slack,
                                      self.weight_sigma, max_iter=self.ipm_max_iter, active=active, retry_failed=True)
-            self.launches += 1
+            self.launches += 2      # the list kernel and the retry pass
         if solver_events is not None:
             solver_events[1].record(torch.cuda.current_stream())
         self._order = _device.order_by_iters(self.ws.iters, out=self._order_buf)
