@@ -27,6 +27,10 @@
 // run longest-first -- scvx_solve_args.block_order.)
 // Best-response (Nash game) terms: diagonal / linear / consecutive-difference quadratics and sigma == sigma_ref, see
 // scvx_solve_args.quad_diag .. fix_sigma in include/scvx_b200.h.
+// Round 2, last session: the iteration's rules beyond textbook Mehrotra -- second-order term weighed by the affine step
+// length (LPs), step fraction rising to 1 - 1e-6 as the centring target vanishes, warm barrier start (scvx_solve_args.mu0) with a cold
+// start where the start point violates a hinge row and a compact retry pass (RETRY instantiation) for the solves that still strand --
+// and the template parameters KT / MT that make the sizes of the BASELINE shapes compile-time constants (solver_*_fixed.cu).
 #pragma once
 #include <cooperative_groups.h>
 
