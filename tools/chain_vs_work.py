@@ -21,5 +21,10 @@ steps = it.shape[0]
 work = it.sum() / steps / 296.0
 agent_chain = it.sum(axis=0).max() / steps
 lane_chain = max(it[:, a:b].max(axis=1).sum() for a, b in lane_bounds(n, lanes)) / steps
+# dealing the agents to the lanes by hardness measured on EARLIER steps (1..2): lane l gets ranks l, l + lanes, l + 2 lanes, ...
+early = out["ipm_iters"].cpu().numpy()[1:3].sum(axis=0)
+order = np.argsort(-early, kind="stable")
+dealt = max(it[:, order[l::lanes]].max(axis=1).sum() for l in range(lanes)) / steps
+print(f"seed {seed}: dealt by early hardness: hardest lane's chain = {dealt:.1f}")
 print(f"seed {seed}: mean iterations/solve {it.mean() - 0.4:.2f}; per step: total work / 296 slots = {work:.1f} iterations, hardest agent's chain = "
       f"{agent_chain:.1f}, hardest of {lanes} lanes' chain = {lane_chain:.1f}; agents above 15 iterations/step on average: {(it.mean(axis=0) > 15).sum()}")
