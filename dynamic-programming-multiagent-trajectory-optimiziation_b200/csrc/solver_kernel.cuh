@@ -807,15 +807,22 @@ next_unit:
       l2_prefetch(ws.dxi + (size_t)ha * K, n * rowb); l2_prefetch(ws.dl1 + (size_t)ha * K, n * rowb); l2_prefetch(ws.dl2 + (size_t)ha * K, n * rowb);
     }
   };
-  // residual pass: the pending step of the hinge pair is applied, in place
+  // residual pass: the pending step of the hinge pair is applied, in place.  Loads and stores are separate calls so that a chunk
+  // issues all of its loads before its first store (ptxas orders a load behind an earlier store it cannot prove disjoint).
   auto load_hinge_apply = [&](int h, int k, double al_p, double al_d) -> HingeData<D> {
     HingeData<D> r = load_hinge_ab(h, k);
     if (r.on) {
       const size_t o = (size_t)h * K + k;
       r.xi = fma(al_p, ws.dxi[o], ws.s.xi[o]); r.l1 = fma(al_d, ws.dl1[o], ws.s.l1[o]); r.l2 = fma(al_d, ws.dl2[o], ws.s.l2[o]);
-      st_na(ws.s.xi + o, r.xi); st_na(ws.s.l1 + o, r.l1); st_na(ws.s.l2 + o, r.l2);
+      if (MT < 0) { st_na(ws.s.xi + o, r.xi); st_na(ws.s.l1 + o, r.l1); st_na(ws.s.l2 + o, r.l2); }      // (see hinge_R_range)
     }
     return r;
+  };
+  auto store_hinge_state = [&](int h, int k, const HingeData<D>& r) {
+    if (r.on) {
+      const size_t o = (size_t)h * K + k;
+      st_na(ws.s.xi + o, r.xi); st_na(ws.s.l1 + o, r.l1); st_na(ws.s.l2 + o, r.l2);
+    }
   };
 
   // ---- load problem data into shared memory ---------------------------------------------------------
@@ -1070,6 +1077,12 @@ next_unit:
         HingeData<D> hb[HINGE_CHUNK];
 #pragma unroll
         for (int c = 0; c < HINGE_CHUNK; ++c) hb[c] = load_hinge_apply(h0 + c, k, al_p0, al_d0);
+        // few hinge rows (the compile-time-M kernels): all stores of the chunk after all of its loads (-5 % on the bench step); with
+        // hundreds of rows per stage (config 4) a pair's stores right behind its loads are better (same-box A/B: 41.3 vs 44.4 ms per round)
+        if (MT >= 0) {
+#pragma unroll
+          for (int c = 0; c < HINGE_CHUNK; ++c) store_hinge_state(h0 + c, k, hb[c]);
+        }
 #pragma unroll
         for (int c = 0; c < HINGE_CHUNK; ++c)
           if (hb[c].on) hinge_R(h0 + c, hb[c], w, Dacc, bt_, bl_);
@@ -1981,13 +1994,35 @@ next_unit:
             const bool fr = (k > 0 && k < K - 1);
 #pragma unroll
             for (int i = 0; i < NS; ++i) W[k * NSP + i] += ap * dW[k * NSP + i];
-            // multipliers of this stage's plain rows, in place (the same rows the passes visit)
+            // multipliers of this stage's plain rows, in place (the same rows the passes visit).  All loads of a chunk are issued
+            // before its first store: written row by row, ptxas cannot prove that the store of one row and the load of the next do
+            // not alias and serialises 20 of the 28 L2 round trips (r02w source page: ~450 stall samples on each of them, 5.3 % of
+            // the kernel's samples on this one statement).
+            constexpr int LCH = 14;
+            if (BALL) {      // (the single-integrator kernels, short of registers, keep the row-by-row form)
 #pragma unroll
-            for (int r = 0; r < NPLAIN; ++r) {
-              const bool visited = (r < NEX) ? (k < K - 1) : ((r < Dm::R_P) ? true : fr);
-              if (visited) {
-                const size_t o = (size_t)r * K + k;
-                st_na(ws.s.lP + o, fma(ad, DLR(r), ws.s.lP[o]));
+              for (int r = 0; r < NPLAIN; ++r) {
+                const bool visited = (r < NEX) ? (k < K - 1) : ((r < Dm::R_P) ? true : fr);
+                if (visited) {
+                  const size_t o = (size_t)r * K + k;
+                  st_na(ws.s.lP + o, fma(ad, DLR(r), ws.s.lP[o]));
+                }
+              }
+            }
+#pragma unroll
+            for (int r0 = 0; r0 < (BALL ? 0 : NPLAIN); r0 += LCH) {
+              double cur[LCH];
+#pragma unroll
+              for (int j = 0; j < LCH; ++j) {
+                const int r = r0 + j;
+                const bool visited = (r < NPLAIN) && ((r < NEX) ? (k < K - 1) : ((r < Dm::R_P) ? true : fr));
+                cur[j] = visited ? ws.s.lP[(size_t)r * K + k] : 0.0;
+              }
+#pragma unroll
+              for (int j = 0; j < LCH; ++j) {
+                const int r = r0 + j;
+                const bool visited = (r < NPLAIN) && ((r < NEX) ? (k < K - 1) : ((r < Dm::R_P) ? true : fr));
+                if (visited) st_na(ws.s.lP + (size_t)r * K + k, fma(ad, DLR(r < NPLAIN ? r : 0), cur[j]));
               }
             }
             if (BALL && fr) st_na(ws.s.sB + k, fma(ap, dsb, ws.s.sB[k]));
