@@ -290,8 +290,8 @@ __device__ __forceinline__ void apply_dinv(const double (*Li)[NS], const double*
 template <class Dm>
 __device__ __forceinline__ void cr_factor(double* A, double* B, double* C, int n, int tid, int nthr) {
   constexpr int NS = Dm::NS, SD = Dm::SD;
-  for (int s = 1; s <= n; s <<= 1) {
-    const int cnt = (n / s + 1) >> 1;            // odd nodes j = s (2m+1) <= n
+  for (int s = 1, ls = 0; s <= n; s <<= 1, ++ls) {       // (ls = log2 s: n / s as a shift -- the stride is a loop variable, a division by it
+    const int cnt = ((n >> ls) + 1) >> 1;        //  costs an integer-division sequence per level and sweep) odd nodes j = s (2m+1) <= n
     const int npr = nthr / NS;                   // nodes per round: the NS columns of a node always share a round
     // One compute section per round: thread (j, c) derives from shared memory -- untouched until the barrier -- the
     // pivot's inverse factor, column c of P_j and Q_j, the push-left update of D_{j-s} and the push-right update of
@@ -394,8 +394,8 @@ __device__ __forceinline__ double* rhs_col(double* Rb, double* dW, int k, int c)
 template <class Dm, int NC>
 __device__ __forceinline__ void cr_forward(const double* B, const double* C, double* Rb, double* dW, int n, int tid, int nthr) {
   constexpr int NS = Dm::NS, SD = Dm::SD;
-  for (int s = 1; 2 * s <= n; s <<= 1) {
-    const int nodes = n / (2 * s);                 // even nodes a = 2 s (m+1)
+  for (int s = 1, ls = 0; 2 * s <= n; s <<= 1, ++ls) {
+    const int nodes = n >> (ls + 1);               // n / (2 s): even nodes a = 2 s (m+1)
     if (NC == 1) {
       for (int it = tid; it < nodes * NS; it += nthr) {
         const int m = it / NS, r = it - m * NS;
@@ -475,10 +475,10 @@ __device__ __forceinline__ void cr_apply_dinv_all(const double* A, double* dW, i
 template <class Dm, int NC>
 __device__ __forceinline__ void cr_backward(const double* B, const double* C, double* Rb, double* dW, int n, int tid, int nthr) {
   constexpr int NS = Dm::NS, SD = Dm::SD;
-  int s = 1;
-  while (2 * s <= n) s <<= 1;
-  for (; s >= 1; s >>= 1) {
-    const int nodes = (n / s + 1) >> 1;            // odd nodes j = s (2m+1)
+  int s = 1, ls = 0;
+  while (2 * s <= n) { s <<= 1; ++ls; }
+  for (; s >= 1; s >>= 1, --ls) {
+    const int nodes = ((n >> ls) + 1) >> 1;        // (n / s + 1) / 2: odd nodes j = s (2m+1)
     if (NC == 1) {
       for (int it = tid; it < nodes * NS; it += nthr) {
         const int m = it / NS, i = it - m * NS;
